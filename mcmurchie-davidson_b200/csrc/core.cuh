@@ -1,0 +1,441 @@
+// core.cuh — device building blocks of the B200 McMurchie-Davidson two-electron engine.
+//
+// What the reference does per basis-function quartet with naive recursion
+// (cython/twoe.pyx:56-94 electron_repulsion, cython/util.pxi:13-50 E and R, util.pxi:54-55 boys)
+// is done here per SHELL quartet:
+//   - Boys F_0..F_L(T): shared-memory-staged Taylor table (step 1/8, 9 terms) for F_L, downward
+//     recursion for the rest, asymptotic + upward recursion for T >= 40;
+//   - Hermite Coulomb integrals R_tuv: one in-place recursion over the auxiliary index n, entirely
+//     in registers for the class-specialised kernels;
+//   - Hermite expansion coefficients E_t^{ij}: per primitive PAIR, rebuilt in registers from
+//     (P-A, P-B, 1/2p), normalised by E_0^{00} (which lives in the pair prefactor);
+//   - ket Hermite->Cartesian transform per primitive quartet, bra transform once per bra
+//     primitive pair after the ket primitives have been summed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+namespace mmdb {
+
+// ------------------------------------------------------------------------------------------
+// compile-time geometry of Cartesian shells and Hermite index sets
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int ncart(int l) { return (l + 1) * (l + 2) / 2; }
+__host__ __device__ constexpr int nherm(int L) { return (L + 1) * (L + 2) * (L + 3) / 6; }
+
+// Cartesian component c of a shell with angular momentum l, reference order
+// (mmd/molecule.py:108-114): p = x,y,z ; d = xx,xy,xz,yy,yz,zz.
+__host__ __device__ constexpr int cart_pow(int l, int c, int dim)
+{
+    int idx = 0;
+    for (int i = l; i >= 0; --i)
+        for (int j = l - i; j >= 0; --j) {
+            if (idx == c) return dim == 0 ? i : (dim == 1 ? j : l - i - j);
+            ++idx;
+        }
+    return 0;
+}
+
+// Packed index of Hermite triple (t,u,v): degree-major, independent of the maximum degree.
+__host__ __device__ constexpr int hidx(int t, int u, int v)
+{
+    const int n = t + u + v;
+    return n * (n + 1) * (n + 2) / 6 + (n - t) * (n - t + 1) / 2 + v;
+}
+
+// 1/sqrt((2l-1)!!(2m-1)!!(2n-1)!!): the per-component part of the primitive norm
+// (cython/basis.pxi:102-105).  Only d has non-trivial values.
+__host__ __device__ constexpr double comp_scale(int l, int c)
+{
+    double s = 1.0;
+    for (int dim = 0; dim < 3; ++dim) {
+        int k = cart_pow(l, c, dim);
+        if (k == 2) s *= 0.57735026918962576451;          // 1/sqrt(3)
+        if (k == 3) s *= 0.25819888974716112568;          // 1/sqrt(15)
+    }
+    return s;
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void sfor(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        sfor<I + 1, N>(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// device-resident tables
+// ------------------------------------------------------------------------------------------
+struct __align__(16) PrimPair {   // one primitive pair of a shell pair, 64 B
+    double Px, Py, Pz, p;          // Gaussian product centre, total exponent
+    double cc;                     // c_a c_b exp(-mu|AB|^2) * sqrt(2) pi^(5/4) / p
+    double PAx, PAy, PAz;          // P - A   (P - B = PA + (A - B))
+};
+
+struct __align__(16) PairHdr {    // one shell pair, 64 B
+    int bfA, bfB;                  // first device function index of shells A, B
+    int poff, pnum;                // primitive-pair range in the class's PrimPair array
+    int shA, shB;                  // shell ids (am[A] >= am[B]; equal am: A >= B)
+    int pad0, pad1;
+    double ABx, ABy, ABz;          // A - B
+    double Qs;                     // max over function pairs sqrt|(pq|pq)|  (filled by mmdb_schwarz)
+};
+
+// Boys table: rows T0 = i/8, i = 0..320; columns k = 0..8: F_{L+k}(T0)/k!, column 9: exp(-T0).
+constexpr int BOYS_ROWS = 321;
+constexpr int BOYS_STRIDE = 10;
+constexpr double BOYS_TMAX = 40.0;
+constexpr int BOYS_MAXL = 8;
+
+// ------------------------------------------------------------------------------------------
+// Boys function  (replaces scipy hyp1f1 of cython/util.pxi:54-55)
+// ------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void boys_eval(double T, const double *__restrict__ tab, double (&F)[L + 1])
+{
+    if (T < BOYS_TMAX) {
+        const int row = __double2int_rn(T * 8.0);
+        const double *r = tab + row * BOYS_STRIDE;
+        const double d = (double)row * 0.125 - T;   // T0 - T, |d| <= 1/16
+        double f = r[8];
+#pragma unroll
+        for (int k = 7; k >= 0; --k) f = fma(f, d, r[k]);
+        F[L] = f;
+        if constexpr (L > 0) {
+            // exp(-T) = exp(-T0) * exp(d)
+            double e = 2.48015873015873015873e-05;   // 1/8!
+            e = fma(e, d, 1.98412698412698412698e-04);
+            e = fma(e, d, 1.38888888888888888889e-03);
+            e = fma(e, d, 8.33333333333333333333e-03);
+            e = fma(e, d, 4.16666666666666666667e-02);
+            e = fma(e, d, 1.66666666666666666667e-01);
+            e = fma(e, d, 0.5);
+            e = fma(e, d, 1.0);
+            e = fma(e, d, 1.0);
+            e *= r[9];
+            const double t2 = T + T;
+            sfor<0, L>([&](auto I) {
+                constexpr int m = L - decltype(I)::value;     // m = L .. 1
+                F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
+            });
+        }
+    } else {
+        const double it = 1.0 / T;
+        F[0] = 0.88622692545275801365 * sqrt(it);             // sqrt(pi)/2 / sqrt(T)
+        if constexpr (L > 0) {
+            const double e = (T < 120.0) ? exp(-T) : 0.0;
+            const double hit = 0.5 * it;
+            sfor<0, L>([&](auto I) {
+                constexpr int m = decltype(I)::value;
+                F[m + 1] = ((2 * m + 1) * F[m] - e) * hit;
+            });
+        }
+    }
+}
+
+// runtime-L version for the generic kernel
+__device__ __forceinline__ void boys_eval_rt(int L, double T, const double *__restrict__ tab, double *F)
+{
+    if (T < BOYS_TMAX) {
+        const int row = __double2int_rn(T * 8.0);
+        const double *r = tab + row * BOYS_STRIDE;
+        const double d = (double)row * 0.125 - T;
+        double f = r[8];
+#pragma unroll
+        for (int k = 7; k >= 0; --k) f = fma(f, d, r[k]);
+        F[L] = f;
+        if (L > 0) {
+            double e = 2.48015873015873015873e-05;
+            e = fma(e, d, 1.98412698412698412698e-04);
+            e = fma(e, d, 1.38888888888888888889e-03);
+            e = fma(e, d, 8.33333333333333333333e-03);
+            e = fma(e, d, 4.16666666666666666667e-02);
+            e = fma(e, d, 1.66666666666666666667e-01);
+            e = fma(e, d, 0.5);
+            e = fma(e, d, 1.0);
+            e = fma(e, d, 1.0);
+            e *= r[9];
+            const double t2 = T + T;
+            for (int m = L; m > 0; --m) F[m - 1] = fma(t2, F[m], e) / (double)(2 * m - 1);
+        }
+    } else {
+        const double it = 1.0 / T;
+        F[0] = 0.88622692545275801365 * sqrt(it);
+        if (L > 0) {
+            const double e = (T < 120.0) ? exp(-T) : 0.0;
+            const double hit = 0.5 * it;
+            for (int m = 0; m < L; ++m) F[m + 1] = ((2 * m + 1) * F[m] - e) * hit;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Hermite expansion coefficients, normalised by E_0^{00}  (cython/util.pxi:13-26, n = 0 branch)
+//   E^{i,0}_t = 1/(2p) E^{i-1,0}_{t-1} + (P-A) E^{i-1,0}_t + (t+1) E^{i-1,0}_{t+1}
+//   E^{i,j}_t = 1/(2p) E^{i,j-1}_{t-1} + (P-B) E^{i,j-1}_t + (t+1) E^{i,j-1}_{t+1}
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB>
+struct ETab {
+    double v[3][LA + 1][LB + 1][LA + LB + 1];
+};
+
+template <int LA, int LB>
+__device__ __forceinline__ void build_E(ETab<LA, LB> &E, const double (&PA)[3], const double (&PB)[3], double oo2p)
+{
+    sfor<0, 3>([&](auto DIM) {
+        constexpr int dim = decltype(DIM)::value;
+        E.v[dim][0][0][0] = 1.0;
+        sfor<1, LA + 1>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            sfor<0, i + 1>([&](auto TT) {
+                constexpr int t = decltype(TT)::value;
+                double x = 0.0;
+                if constexpr (t > 0) x = oo2p * E.v[dim][i - 1][0][t - 1];
+                if constexpr (t <= i - 1) x = fma(PA[dim], E.v[dim][i - 1][0][t], x);
+                if constexpr (t + 1 <= i - 1) x = fma((double)(t + 1), E.v[dim][i - 1][0][t + 1], x);
+                E.v[dim][i][0][t] = x;
+            });
+        });
+        sfor<1, LB + 1>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            sfor<0, LA + 1>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                sfor<0, i + j + 1>([&](auto TT) {
+                    constexpr int t = decltype(TT)::value;
+                    double x = 0.0;
+                    if constexpr (t > 0) x = oo2p * E.v[dim][i][j - 1][t - 1];
+                    if constexpr (t <= i + j - 1) x = fma(PB[dim], E.v[dim][i][j - 1][t], x);
+                    if constexpr (t + 1 <= i + j - 1) x = fma((double)(t + 1), E.v[dim][i][j - 1][t + 1], x);
+                    E.v[dim][i][j][t] = x;
+                });
+            });
+        });
+    });
+}
+
+// ------------------------------------------------------------------------------------------
+// Hermite Coulomb integrals R^0_{tuv}, t+u+v <= L  (cython/util.pxi:33-50), in place over n.
+// Fs[n] = prefactor * (-2 alpha)^n F_n(T) on entry.  Same branch order as the reference:
+// lower t if t > 0, else u if u > 0, else v.
+// ------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void build_R(double (&R)[nherm(L)], const double (&Fs)[L + 1], double X, double Y, double Z)
+{
+    R[0] = Fs[L];
+    sfor<0, L>([&](auto NN) {
+        constexpr int n = L - 1 - decltype(NN)::value;   // n = L-1 .. 0
+        sfor<0, L - n>([&](auto DD) {
+            constexpr int d = (L - n) - decltype(DD)::value;   // degree d = L-n .. 1
+            sfor<0, d + 1>([&](auto TT) {
+                constexpr int t = d - decltype(TT)::value;
+                sfor<0, d - t + 1>([&](auto UU) {
+                    constexpr int u = (d - t) - decltype(UU)::value;
+                    constexpr int v = d - t - u;
+                    double x;
+                    if constexpr (t > 0) {
+                        x = X * R[hidx(t - 1, u, v)];
+                        if constexpr (t > 1) x = fma((double)(t - 1), R[hidx(t - 2, u, v)], x);
+                    } else if constexpr (u > 0) {
+                        x = Y * R[hidx(t, u - 1, v)];
+                        if constexpr (u > 1) x = fma((double)(u - 1), R[hidx(t, u - 2, v)], x);
+                    } else {
+                        x = Z * R[hidx(t, u, v - 1)];
+                        if constexpr (v > 1) x = fma((double)(v - 1), R[hidx(t, u, v - 2)], x);
+                    }
+                    R[hidx(t, u, v)] = x;
+                });
+            });
+        });
+        R[0] = Fs[n];
+    });
+}
+
+// ------------------------------------------------------------------------------------------
+// One contracted shell quartet, ket component pairs [CD0, CD0+NCDC), class-specialised.
+// out[ab*NCDC + cdi] accumulates (ab|cd) WITHOUT the per-component normalisation.
+// ------------------------------------------------------------------------------------------
+template <int LA, int LB, int LC, int LD, int CD0, int NCDC>
+__device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const PrimPair *__restrict__ bp,
+                                                   const PairHdr &kh, const PrimPair *__restrict__ kp,
+                                                   const double *__restrict__ boys_tab,
+                                                   double (&out)[ncart(LA) * ncart(LB) * NCDC])
+{
+    constexpr int LBRA = LA + LB, LKET = LC + LD, L = LBRA + LKET;
+    constexpr int NA = ncart(LA), NB = ncart(LB), ND = ncart(LD);
+    constexpr int NAB = NA * NB;
+    constexpr int NHB = nherm(LBRA);
+
+#pragma unroll
+    for (int x = 0; x < NAB * NCDC; ++x) out[x] = 0.0;
+
+    for (int ib = 0; ib < bh.pnum; ++ib) {
+        const PrimPair b = bp[bh.poff + ib];
+        ETab<LA, LB> Eb;
+        {
+            const double PA[3] = {b.PAx, b.PAy, b.PAz};
+            const double PB[3] = {b.PAx + bh.ABx, b.PAy + bh.ABy, b.PAz + bh.ABz};
+            build_E<LA, LB>(Eb, PA, PB, 0.5 / b.p);
+        }
+        double G[NHB * NCDC];
+#pragma unroll
+        for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
+
+        for (int ik = 0; ik < kh.pnum; ++ik) {
+            const PrimPair k = kp[kh.poff + ik];
+            const double pq = b.p + k.p;
+            const double ipq = 1.0 / pq;
+            const double alpha = b.p * k.p * ipq;
+            const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
+            const double T = alpha * (X * X + Y * Y + Z * Z);
+            double Fs[L + 1];
+            boys_eval<L>(T, boys_tab, Fs);
+            {
+                double s = b.cc * k.cc * sqrt(ipq);   // 2 pi^2.5 /(p q sqrt(p+q)) * c's * K's
+                const double m2a = -2.0 * alpha;
+#pragma unroll
+                for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
+            }
+            double R[nherm(L)];
+            build_R<L>(R, Fs, X, Y, Z);
+
+            ETab<LC, LD> Ek;
+            {
+                const double QC[3] = {k.PAx, k.PAy, k.PAz};
+                const double QD[3] = {k.PAx + kh.ABx, k.PAy + kh.ABy, k.PAz + kh.ABz};
+                build_E<LC, LD>(Ek, QC, QD, 0.5 / k.p);
+            }
+            // ket Hermite -> Cartesian:  G[tuv][cd] += (-1)^(tau+nu+phi) E^cd_tau E^cd_nu E^cd_phi R[t+tau,u+nu,v+phi]
+            sfor<0, NCDC>([&](auto CDI) {
+                constexpr int cdi = decltype(CDI)::value;
+                constexpr int cd = CD0 + cdi;
+                constexpr int c = cd / ND, d = cd % ND;
+                constexpr int cx = cart_pow(LC, c, 0), cy = cart_pow(LC, c, 1), cz = cart_pow(LC, c, 2);
+                constexpr int dx = cart_pow(LD, d, 0), dy = cart_pow(LD, d, 1), dz = cart_pow(LD, d, 2);
+                sfor<0, cx + dx + 1>([&](auto TAU) {
+                    constexpr int tau = decltype(TAU)::value;
+                    sfor<0, cy + dy + 1>([&](auto NU) {
+                        constexpr int nu = decltype(NU)::value;
+                        const double exy = Ek.v[0][cx][dx][tau] * Ek.v[1][cy][dy][nu];
+                        sfor<0, cz + dz + 1>([&](auto PHI) {
+                            constexpr int phi = decltype(PHI)::value;
+                            double coef = exy * Ek.v[2][cz][dz][phi];
+                            if constexpr ((tau + nu + phi) & 1) coef = -coef;
+                            sfor<0, LBRA + 1>([&](auto TT) {
+                                constexpr int t = decltype(TT)::value;
+                                sfor<0, LBRA - t + 1>([&](auto UU) {
+                                    constexpr int u = decltype(UU)::value;
+                                    sfor<0, LBRA - t - u + 1>([&](auto VV) {
+                                        constexpr int v = decltype(VV)::value;
+                                        G[hidx(t, u, v) * NCDC + cdi] =
+                                            fma(coef, R[hidx(t + tau, u + nu, v + phi)], G[hidx(t, u, v) * NCDC + cdi]);
+                                    });
+                                });
+                            });
+                        });
+                    });
+                });
+            });
+        }
+        // bra Hermite -> Cartesian:  out[ab][cd] += E^ab_t E^ab_u E^ab_v G[tuv][cd]
+        sfor<0, NAB>([&](auto ABI) {
+            constexpr int ab = decltype(ABI)::value;
+            constexpr int a = ab / NB, bb = ab % NB;
+            constexpr int ax = cart_pow(LA, a, 0), ay = cart_pow(LA, a, 1), az = cart_pow(LA, a, 2);
+            constexpr int bx = cart_pow(LB, bb, 0), by = cart_pow(LB, bb, 1), bz = cart_pow(LB, bb, 2);
+            sfor<0, ax + bx + 1>([&](auto TT) {
+                constexpr int t = decltype(TT)::value;
+                sfor<0, ay + by + 1>([&](auto UU) {
+                    constexpr int u = decltype(UU)::value;
+                    const double exy = Eb.v[0][ax][bx][t] * Eb.v[1][ay][by][u];
+                    sfor<0, az + bz + 1>([&](auto VV) {
+                        constexpr int v = decltype(VV)::value;
+                        const double coef = exy * Eb.v[2][az][bz][v];
+#pragma unroll
+                        for (int cdi = 0; cdi < NCDC; ++cdi)
+                            out[ab * NCDC + cdi] = fma(coef, G[hidx(t, u, v) * NCDC + cdi], out[ab * NCDC + cdi]);
+                    });
+                });
+            });
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Digestion of one contracted basis-function integral (ij|kl) into G  (cython/fock.pyx:38-85).
+// ------------------------------------------------------------------------------------------
+struct DigestArgs {
+    int N;
+    double tol;
+    const double *SQ;      // sqrt((pq|pq)) (N,N)
+    const double *Dabs;    // |dP| (N,N)
+    const double *dPre;    // Re dP (N,N)
+    const double *dPim;    // Im dP or nullptr
+    double *Gre;
+    double *Gim;           // or nullptr
+};
+
+__device__ __forceinline__ void digest_fn_quartet(const DigestArgs &g, int i, int j, int k, int l, bool sameAB,
+                                                  bool sameCD, bool samePair, double val)
+{
+    // each canonical function quartet i>=j, k>=l, ij>=kl exactly once
+    if (sameAB && i < j) return;
+    if (sameCD && k < l) return;
+    if (i < j) { int t = i; i = j; j = t; }
+    if (k < l) { int t = k; k = l; l = t; }
+    const long long ij = (long long)i * (i + 1) / 2 + j, kl = (long long)k * (k + 1) / 2 + l;
+    if (ij < kl) {
+        if (samePair) return;
+        int t = i; i = k; k = t;
+        t = j; j = l; l = t;
+    }
+    const int N = g.N;
+    const double *D = g.Dabs;
+    double bound = g.SQ[i * N + j] * g.SQ[k * N + l];                       // fock.pyx:46-47
+    double dmax = fmax(4.0 * D[i * N + j], 4.0 * D[k * N + l]);             // fock.pyx:49-54
+    dmax = fmax(dmax, fmax(fmax(D[i * N + k], D[i * N + l]), fmax(D[j * N + k], D[j * N + l])));
+    bound *= dmax;
+    if (bound < g.tol) return;                                              // fock.pyx:56-57
+    double deg = (i == j) ? 1.0 : 2.0;                                      // fock.pyx:60-70
+    if (k != l) deg *= 2.0;
+    if (!(i == k && j == l)) deg *= 2.0;
+    const double e = deg * val;                                            // fock.pyx:74-75
+    const double eq = -0.25 * e;
+    const double *P = g.dPre;
+    atomicAdd(&g.Gre[i * N + j], P[k * N + l] * e);                         // fock.pyx:79
+    atomicAdd(&g.Gre[k * N + l], P[i * N + j] * e);                         // fock.pyx:80
+    atomicAdd(&g.Gre[i * N + k], P[j * N + l] * eq);                        // fock.pyx:82
+    atomicAdd(&g.Gre[j * N + l], P[i * N + k] * eq);                        // fock.pyx:83
+    atomicAdd(&g.Gre[i * N + l], P[j * N + k] * eq);                        // fock.pyx:84
+    atomicAdd(&g.Gre[k * N + j], P[i * N + l] * eq);                        // fock.pyx:85
+    if (g.dPim != nullptr) {
+        const double *Q = g.dPim;
+        atomicAdd(&g.Gim[i * N + j], Q[k * N + l] * e);
+        atomicAdd(&g.Gim[k * N + l], Q[i * N + j] * e);
+        atomicAdd(&g.Gim[i * N + k], Q[j * N + l] * eq);
+        atomicAdd(&g.Gim[j * N + l], Q[i * N + k] * eq);
+        atomicAdd(&g.Gim[i * N + l], Q[j * N + k] * eq);
+        atomicAdd(&g.Gim[k * N + j], Q[i * N + l] * eq);
+    }
+}
+
+// Arguments of the ERI kernels (both families).
+struct EriArgs {
+    const PairHdr *braH;
+    const PrimPair *braP;
+    const PairHdr *ketH;
+    const PrimPair *ketP;
+    const uint2 *list;            // (bra pair, ket pair) per entry
+    const unsigned long long *count_dev;   // number of entries (device) or nullptr -> use n
+    unsigned long long n;
+    const double *boys_tab;       // [BOYS_ROWS][BOYS_STRIDE] for this class's L (global)
+    double *out;                  // EPI_STORE: [entry][nfn]
+    int same_class;               // bra class == ket class (entries with .x == .y are diagonal quartets)
+    DigestArgs dg;                // EPI_DIGEST
+};
+
+enum { EPI_STORE = 0, EPI_DIGEST = 1 };
+
+}  // namespace mmdb

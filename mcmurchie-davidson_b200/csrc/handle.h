@@ -1,0 +1,68 @@
+// handle.h — the opaque mmdb_basis handle and error plumbing shared by the host translation units.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/mmdb200.h"
+#include "core.cuh"
+
+extern thread_local std::string mmdb_g_err;
+static inline int fail(int code, const std::string &msg)
+{
+    mmdb_g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(MMDB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                                           std::to_string(__LINE__) + ")");                               \
+    } while (0)
+#define CHK(call)                   \
+    do {                            \
+        int _r = (call);            \
+        if (_r != MMDB_OK) return _r; \
+    } while (0)
+
+struct ShellH {
+    int am, nprim, poff, bf0;
+    double x, y, z;
+};
+
+struct PairClass {
+    int la = 0, lb = 0;
+    int npairs = 0;
+    int64_t nprimpairs = 0;
+    std::vector<mmdb::PairHdr> hdr;
+    std::vector<mmdb::PrimPair> prim;
+    mmdb::PairHdr *hdr_dev = nullptr;
+    mmdb::PrimPair *prim_dev = nullptr;
+    double *Qs_dev = nullptr;   // [npairs]
+    int *K_dev = nullptr;       // [npairs] primitive pairs per shell pair
+    int2 *sh_dev = nullptr;     // [npairs] (shA, shB)
+};
+
+struct mmdb_basis {
+    int device = 0;
+    int nshell = 0, nbf = 0;
+    int nsm = 148;
+    std::vector<ShellH> sh;
+    std::vector<double> exps, coefs;
+    PairClass pc[MMDB_NCLASS_PAIR];
+    double *boys_dev[mmdb::BOYS_MAXL + 1] = {nullptr};
+    int *sh_bf0_dev = nullptr, *sh_nf_dev = nullptr;
+    double *Q_dev = nullptr, *SQ_dev = nullptr;   // (N,N)
+    bool have_schwarz = false;
+    double *Dabs_dev = nullptr;                   // (N,N)
+    double *DS_dev = nullptr;                     // (nshell,nshell)
+    unsigned long long *dglob_dev = nullptr;      // max|dP| as bits
+    uint2 *list_dev = nullptr;
+    size_t list_cap = 0;
+    unsigned long long *ctr_dev = nullptr;        // counters
+    int nctr = 0;
+    double *scratch_dev = nullptr;
+    size_t scratch_cap = 0;   // doubles
+};
+

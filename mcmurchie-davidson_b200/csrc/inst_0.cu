@@ -1,0 +1,9 @@
+// explicit instantiations of the class-specialised shell-quartet kernels (split for parallel compilation)
+#include "kernels_a.cuh"
+namespace mmdb {
+MMDB_INSTANTIATE_CLASS(0, 0, 0, 0)
+MMDB_INSTANTIATE_CLASS(1, 0, 0, 0)
+MMDB_INSTANTIATE_CLASS(1, 0, 1, 0)
+MMDB_INSTANTIATE_CLASS(1, 1, 0, 0)
+MMDB_INSTANTIATE_CLASS(2, 0, 0, 0)
+}

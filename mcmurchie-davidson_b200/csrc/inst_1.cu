@@ -1,0 +1,6 @@
+// explicit instantiations of the class-specialised shell-quartet kernels (split for parallel compilation)
+#include "kernels_a.cuh"
+namespace mmdb {
+MMDB_INSTANTIATE_CLASS(1, 1, 1, 0)
+MMDB_INSTANTIATE_CLASS(1, 1, 1, 1)
+}

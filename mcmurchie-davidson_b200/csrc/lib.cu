@@ -1,0 +1,846 @@
+// lib.cu — host side of libmmdb200.so: C ABI (include/mmdb200.h), shell-pair tables, screening,
+// class dispatch, Schwarz table, dense fill, direct Fock build driver.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mmdb200.h"
+#include "kernels_a.cuh"
+#include "kernels_b.cuh"
+#include "handle.h"
+
+using namespace mmdb;
+
+thread_local std::string mmdb_g_err;
+
+extern "C" const char *mmdb_last_error(void) { return mmdb_g_err.c_str(); }
+extern "C" int mmdb_version(void) { return 100; }
+extern "C" int mmdb_device_count(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(MMDB_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return MMDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FLOP model of SURVEY.md §8(d)
+// ------------------------------------------------------------------------------------------
+static int S_pair(int la, int lb)
+{
+    int s = 0;
+    for (int a = 0; a < ncart(la); ++a)
+        for (int b = 0; b < ncart(lb); ++b)
+            s += (cart_pow(la, a, 0) + cart_pow(lb, b, 0) + 1) * (cart_pow(la, a, 1) + cart_pow(lb, b, 1) + 1) *
+                 (cart_pow(la, a, 2) + cart_pow(lb, b, 2) + 1);
+    return s;
+}
+extern "C" double mmdb_class_flops(int la, int lb, int lc, int ld)
+{
+    const int Lb = la + lb, Lk = lc + ld, L = Lb + Lk;
+    (void)Lk;
+    int NR = 0;
+    for (int n = 0; n < L; ++n) NR += nherm(L - n) - 1;
+    const int nab = ncart(la) * ncart(lb), ncd = ncart(lc) * ncart(ld);
+    return 30.0 + (20 + 3 * L) + 2 * L + 3.0 * NR + 2.0 * S_pair(lc, ld) * (nherm(Lb) + 1) +
+           2.0 * S_pair(la, lb) * (ncd + 1) + (double)nab * ncd;
+}
+
+// ------------------------------------------------------------------------------------------
+// Boys tables (host, long double): F_m(T0) = exp(-T0) sum_k (2T0)^k / ((2m+1)(2m+3)...(2m+2k+1)),
+// top m by series, the rest by downward recursion.
+// ------------------------------------------------------------------------------------------
+static void boys_ref_ld(int mmax, long double T, long double *F)
+{
+    long double term = 1.0L / (2.0L * mmax + 1.0L), sum = term;
+    for (int k = 1; k < 4000; ++k) {
+        term *= 2.0L * T / (2.0L * mmax + 2.0L * k + 1.0L);
+        sum += term;
+        if (term < 1e-22L * sum) break;
+    }
+    const long double eT = expl(-T);
+    F[mmax] = eT * sum;
+    for (int m = mmax; m > 0; --m) F[m - 1] = (2.0L * T * F[m] + eT) / (2.0L * m - 1.0L);
+}
+
+static void make_boys_table(int L, std::vector<double> &tab)
+{
+    tab.assign((size_t)BOYS_ROWS * BOYS_STRIDE, 0.0);
+    long double F[BOYS_MAXL + 9 + 1];
+    for (int r = 0; r < BOYS_ROWS; ++r) {
+        const long double T0 = (long double)r * 0.125L;
+        boys_ref_ld(L + 8, T0, F);
+        long double fact = 1.0L;
+        for (int k = 0; k <= 8; ++k) {
+            if (k > 0) fact *= k;
+            tab[(size_t)r * BOYS_STRIDE + k] = (double)(F[L + k] / fact);
+        }
+        tab[(size_t)r * BOYS_STRIDE + 9] = (double)expl(-T0);
+    }
+}
+
+static inline int pc_index(int la, int lb) { return la * (la + 1) / 2 + lb; }
+
+static int ensure_list(mmdb_basis *b, size_t entries)
+{
+    if (entries <= b->list_cap) return MMDB_OK;
+    if (b->list_dev) cudaFree(b->list_dev);
+    b->list_dev = nullptr;
+    b->list_cap = 0;
+    CU(cudaMalloc(&b->list_dev, entries * sizeof(uint2)));
+    b->list_cap = entries;
+    return MMDB_OK;
+}
+static int ensure_scratch(mmdb_basis *b, size_t doubles)
+{
+    if (doubles <= b->scratch_cap) return MMDB_OK;
+    if (b->scratch_dev) cudaFree(b->scratch_dev);
+    b->scratch_dev = nullptr;
+    b->scratch_cap = 0;
+    CU(cudaMalloc(&b->scratch_dev, doubles * sizeof(double)));
+    b->scratch_cap = doubles;
+    return MMDB_OK;
+}
+
+extern "C" int mmdb_basis_destroy(mmdb_basis *b)
+{
+    if (!b) return MMDB_OK;
+    cudaSetDevice(b->device);
+    for (auto &p : b->pc) {
+        cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.Qs_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
+    }
+    for (auto &t : b->boys_dev) cudaFree(t);
+    cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
+    cudaFree(b->Dabs_dev); cudaFree(b->DS_dev); cudaFree(b->dglob_dev); cudaFree(b->list_dev);
+    cudaFree(b->ctr_dev); cudaFree(b->scratch_dev);
+    delete b;
+    return MMDB_OK;
+}
+
+extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const int *nprim, const int *prim_off,
+                                 const double *centre, const double *exps, const double *coefs, const int *bf0,
+                                 double prim_cut, mmdb_basis **out)
+{
+    if (!out || nshell <= 0) return fail(MMDB_ERR_INVALID, "mmdb_basis_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MMDB_ERR_CUDA, "mmdb_basis_create: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(MMDB_ERR_INVALID, "mmdb_basis_create: device out of range");
+    CU(cudaSetDevice(device));
+    mmdb_basis *b = new mmdb_basis();
+    b->device = device;
+    b->nshell = nshell;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    b->nsm = prop.multiProcessorCount;
+    int ntot = 0, nbf = 0;
+    for (int s = 0; s < nshell; ++s) {
+        if (am[s] < 0 || am[s] > MMDB_MAX_AM) {
+            delete b;
+            return fail(MMDB_ERR_UNSUPPORTED, "mmdb_basis_create: angular momentum > d is not supported on the device path");
+        }
+        ShellH h{am[s], nprim[s], prim_off[s], bf0[s], centre[3 * s], centre[3 * s + 1], centre[3 * s + 2]};
+        b->sh.push_back(h);
+        ntot = std::max(ntot, prim_off[s] + nprim[s]);
+        nbf = std::max(nbf, bf0[s] + ncart(am[s]));
+    }
+    b->nbf = nbf;
+    b->exps.assign(exps, exps + ntot);
+    b->coefs.assign(coefs, coefs + ntot);
+
+    // ---- shell pairs, by class; am[A] >= am[B], equal am: A >= B --------------------------------
+    const double SQRT2_PI54 = std::sqrt(2.0) * std::pow(M_PI, 1.25);
+    for (int la = 0; la <= MMDB_MAX_AM; ++la)
+        for (int lb = 0; lb <= la; ++lb) {
+            PairClass &P = b->pc[pc_index(la, lb)];
+            P.la = la;
+            P.lb = lb;
+        }
+    struct Tmp {
+        PairHdr h;
+        std::vector<PrimPair> pp;
+    };
+    std::vector<Tmp> tmp[MMDB_NCLASS_PAIR];
+    for (int A = 0; A < nshell; ++A)
+        for (int B = 0; B <= A; ++B) {
+            int a = A, c = B;
+            if (b->sh[a].am < b->sh[c].am) std::swap(a, c);
+            const ShellH &sa = b->sh[a], &sb = b->sh[c];
+            const double ABx = sa.x - sb.x, ABy = sa.y - sb.y, ABz = sa.z - sb.z;
+            const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
+            Tmp t;
+            std::memset(&t.h, 0, sizeof(PairHdr));
+            t.h.bfA = sa.bf0; t.h.bfB = sb.bf0; t.h.shA = a; t.h.shB = c;
+            t.h.ABx = ABx; t.h.ABy = ABy; t.h.ABz = ABz; t.h.Qs = 0.0;
+            const int lab = sa.am + sb.am;
+            for (int i = 0; i < sa.nprim; ++i)
+                for (int j = 0; j < sb.nprim; ++j) {
+                    const double ea = b->exps[sa.poff + i], eb = b->exps[sb.poff + j];
+                    const double p = ea + eb, mu = ea * eb / p;
+                    const double K = std::exp(-mu * AB2);
+                    const double c2 = b->coefs[sa.poff + i] * b->coefs[sb.poff + j];
+                    if (prim_cut > 0) {
+                        // magnitude estimate: sqrt of the primitive (ss|ss)-like self repulsion, with a
+                        // generous polynomial allowance for the angular factors
+                        double est = std::fabs(c2) * K * std::pow(M_PI, 1.25) * std::pow(2.0, 0.25) / std::pow(p, 1.25);
+                        est *= std::pow(1.0 + std::sqrt(AB2), lab) * std::pow(std::max(1.0, p), 0.5 * lab) * 16.0;
+                        if (est < prim_cut) continue;
+                    }
+                    PrimPair q;
+                    q.p = p;
+                    q.Px = (ea * sa.x + eb * sb.x) / p;
+                    q.Py = (ea * sa.y + eb * sb.y) / p;
+                    q.Pz = (ea * sa.z + eb * sb.z) / p;
+                    q.PAx = q.Px - sa.x; q.PAy = q.Py - sa.y; q.PAz = q.Pz - sa.z;
+                    q.cc = c2 * K * SQRT2_PI54 / p;
+                    t.pp.push_back(q);
+                }
+            if (t.pp.empty()) continue;
+            t.h.pnum = (int)t.pp.size();
+            tmp[pc_index(sa.am, sb.am)].push_back(std::move(t));
+        }
+    for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
+        PairClass &P = b->pc[c];
+        auto &v = tmp[c];
+        // homogeneous contraction depth inside a warp: order by primitive-pair count (desc), stable
+        std::stable_sort(v.begin(), v.end(), [](const Tmp &x, const Tmp &y) { return x.h.pnum > y.h.pnum; });
+        P.npairs = (int)v.size();
+        for (auto &t : v) {
+            t.h.poff = (int)P.prim.size();
+            P.prim.insert(P.prim.end(), t.pp.begin(), t.pp.end());
+            P.hdr.push_back(t.h);
+        }
+        P.nprimpairs = (int64_t)P.prim.size();
+        if (P.npairs == 0) continue;
+        std::vector<int> K(P.npairs);
+        std::vector<int2> shs(P.npairs);
+        for (int i = 0; i < P.npairs; ++i) {
+            K[i] = P.hdr[i].pnum;
+            shs[i] = make_int2(P.hdr[i].shA, P.hdr[i].shB);
+        }
+        CU(cudaMalloc(&P.hdr_dev, sizeof(PairHdr) * P.npairs));
+        CU(cudaMalloc(&P.prim_dev, sizeof(PrimPair) * P.prim.size()));
+        CU(cudaMalloc(&P.Qs_dev, sizeof(double) * P.npairs));
+        CU(cudaMalloc(&P.K_dev, sizeof(int) * P.npairs));
+        CU(cudaMalloc(&P.sh_dev, sizeof(int2) * P.npairs));
+        CU(cudaMemcpy(P.hdr_dev, P.hdr.data(), sizeof(PairHdr) * P.npairs, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.prim_dev, P.prim.data(), sizeof(PrimPair) * P.prim.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemset(P.Qs_dev, 0, sizeof(double) * P.npairs));
+        CU(cudaMemcpy(P.K_dev, K.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.sh_dev, shs.data(), sizeof(int2) * P.npairs, cudaMemcpyHostToDevice));
+    }
+    // ---- Boys tables --------------------------------------------------------------------------
+    for (int L = 0; L <= BOYS_MAXL; ++L) {
+        std::vector<double> tab;
+        make_boys_table(L, tab);
+        CU(cudaMalloc(&b->boys_dev[L], tab.size() * sizeof(double)));
+        CU(cudaMemcpy(b->boys_dev[L], tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // ---- shell meta, matrices, counters -------------------------------------------------------
+    {
+        std::vector<int> f0(nshell), nf(nshell);
+        for (int s = 0; s < nshell; ++s) { f0[s] = b->sh[s].bf0; nf[s] = ncart(b->sh[s].am); }
+        CU(cudaMalloc(&b->sh_bf0_dev, sizeof(int) * nshell));
+        CU(cudaMalloc(&b->sh_nf_dev, sizeof(int) * nshell));
+        CU(cudaMemcpy(b->sh_bf0_dev, f0.data(), sizeof(int) * nshell, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(b->sh_nf_dev, nf.data(), sizeof(int) * nshell, cudaMemcpyHostToDevice));
+    }
+    const size_t N2 = (size_t)nbf * nbf;
+    CU(cudaMalloc(&b->Q_dev, N2 * sizeof(double)));
+    CU(cudaMalloc(&b->SQ_dev, N2 * sizeof(double)));
+    CU(cudaMalloc(&b->Dabs_dev, N2 * sizeof(double)));
+    CU(cudaMalloc(&b->DS_dev, (size_t)nshell * nshell * sizeof(double)));
+    CU(cudaMalloc(&b->dglob_dev, sizeof(unsigned long long)));
+    b->nctr = 4096;
+    CU(cudaMalloc(&b->ctr_dev, sizeof(unsigned long long) * b->nctr));
+    *out = b;
+    return MMDB_OK;
+}
+
+extern "C" int mmdb_basis_nbf(const mmdb_basis *b, int *nbf)
+{
+    *nbf = b->nbf;
+    return MMDB_OK;
+}
+extern "C" int mmdb_basis_pair_counts(const mmdb_basis *b, int64_t *npairs, int64_t *nprimpairs)
+{
+    for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
+        npairs[c] = b->pc[c].npairs;
+        nprimpairs[c] = b->pc[c].nprimpairs;
+    }
+    return MMDB_OK;
+}
+extern "C" int mmdb_basis_pair_shells(const mmdb_basis *b, int pc, int *shA, int *shB)
+{
+    if (pc < 0 || pc >= MMDB_NCLASS_PAIR) return fail(MMDB_ERR_INVALID, "pair class out of range");
+    const PairClass &P = b->pc[pc];
+    for (int i = 0; i < P.npairs; ++i) {
+        shA[i] = P.hdr[i].shA;
+        shB[i] = P.hdr[i].shB;
+    }
+    return MMDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// class dispatch
+// ------------------------------------------------------------------------------------------
+namespace mmdb {
+#define DECL(LA, LB, LC, LD) \
+    template <>              \
+    cudaError_t launch_class<LA, LB, LC, LD>(const EriArgs &, int, int, cudaStream_t);
+DECL(0, 0, 0, 0) DECL(1, 0, 0, 0) DECL(1, 0, 1, 0) DECL(1, 1, 0, 0) DECL(1, 1, 1, 0) DECL(1, 1, 1, 1)
+DECL(2, 0, 0, 0) DECL(2, 0, 1, 0) DECL(2, 0, 1, 1) DECL(2, 0, 2, 0)
+DECL(2, 1, 0, 0) DECL(2, 1, 1, 0) DECL(2, 1, 1, 1) DECL(2, 1, 2, 0)
+DECL(2, 2, 0, 0) DECL(2, 2, 1, 0)
+#undef DECL
+}  // namespace mmdb
+
+static bool has_class_kernel(int la, int lb, int lc, int ld) { return la + lb + lc + ld <= 5; }
+
+// (la lb) >= (lc ld) in pair-class order is required
+static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a, int epi, int impl, cudaStream_t st)
+{
+    const int L = la + lb + lc + ld;
+    a.boys_tab = b->boys_dev[L];
+    const int key = ((la * 3 + lb) * 3 + lc) * 3 + ld;
+    cudaError_t e = cudaSuccess;
+    const int gridA = b->nsm * 8;
+    if (impl == 0 && has_class_kernel(la, lb, lc, ld)) {
+        switch (key) {
+#define CASE(LA, LB, LC, LD)                                  \
+    case ((LA * 3 + LB) * 3 + LC) * 3 + LD:                   \
+        e = launch_class<LA, LB, LC, LD>(a, epi, gridA, st);  \
+        break;
+            CASE(0, 0, 0, 0) CASE(1, 0, 0, 0) CASE(1, 0, 1, 0) CASE(1, 1, 0, 0) CASE(1, 1, 1, 0) CASE(1, 1, 1, 1)
+            CASE(2, 0, 0, 0) CASE(2, 0, 1, 0) CASE(2, 0, 1, 1) CASE(2, 0, 2, 0)
+            CASE(2, 1, 0, 0) CASE(2, 1, 1, 0) CASE(2, 1, 1, 1) CASE(2, 1, 2, 0)
+            CASE(2, 2, 0, 0) CASE(2, 2, 1, 0)
+#undef CASE
+            default:
+                return fail(MMDB_ERR_INVALID, "launch_eri: class not instantiated");
+        }
+    } else {
+        const size_t smem = BOYS_ROWS * BOYS_STRIDE * sizeof(double);
+        const int grid = b->nsm * 8;
+        if (epi == EPI_STORE)
+            eri_generic_kernel<EPI_STORE><<<grid, KB_THREADS, smem, st>>>(a, la, lb, lc, ld);
+        else
+            eri_generic_kernel<EPI_DIGEST><<<grid, KB_THREADS, smem, st>>>(a, la, lb, lc, ld);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return fail(MMDB_ERR_CUDA, std::string("ERI kernel launch: ") + cudaGetErrorString(e));
+    return MMDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+__global__ void zip_list_kernel(const int32_t *bi, const int32_t *ki, int64_t n, uint2 *list)
+{
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x)
+        list[x] = make_uint2((unsigned)bi[x], (unsigned)ki[x]);
+}
+
+__global__ void diag_list_kernel(int n, uint2 *list)
+{
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) list[x] = make_uint2(x, x);
+}
+
+// Schwarz extraction: scratch[i][ab*nab+ab] -> Q, SQ, Qs
+__global__ void schwarz_extract_kernel(const PairHdr *hdr, int npairs, int la, int lb, const double *scratch, int N,
+                                       double *Q, double *SQ, double *Qs)
+{
+    const int na = ncart(la), nb = ncart(lb), nab = na * nb;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const PairHdr h = hdr[i];
+        double qmax = 0.0;
+        for (int ab = 0; ab < nab; ++ab) {
+            const double v = scratch[(size_t)i * nab * nab + (size_t)ab * nab + ab];
+            const int p = h.bfA + ab / nb, q = h.bfB + ab % nb;
+            Q[(size_t)p * N + q] = v;
+            Q[(size_t)q * N + p] = v;
+            const double s = sqrt(v);   // NaN for (numerically) negative values, like the reference
+            SQ[(size_t)p * N + q] = s;
+            SQ[(size_t)q * N + p] = s;
+            qmax = fmax(qmax, sqrt(fabs(v)));
+        }
+        Qs[i] = qmax;
+    }
+}
+
+__global__ void dabs_kernel(const double *re, const double *im, size_t n, double *out)
+{
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x)
+        out[x] = im ? hypot(re[x], im[x]) : fabs(re[x]);
+}
+
+// shell-block maxima of |dP| and the global maximum
+__global__ void dshell_kernel(const double *Dabs, int N, const int *bf0, const int *nf, int nshell, double *DS,
+                              unsigned long long *dglob)
+{
+    const int total = nshell * nshell;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
+        const int A = x / nshell, B = x % nshell;
+        double m = 0.0;
+        for (int a = 0; a < nf[A]; ++a)
+            for (int c = 0; c < nf[B]; ++c) m = fmax(m, Dabs[(size_t)(bf0[A] + a) * N + bf0[B] + c]);
+        DS[x] = m;
+        atomicMax(dglob, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// Shell-level screen -> compact quartet list.  One warp-wide ballot per 32 candidates.
+// Rows i in [row0,row1) with i % nshards == shard; candidates j < nket (j <= i when same_class).
+struct ScreenArgs {
+    const double *Qs_bra, *Qs_ket;
+    const int2 *sh_bra, *sh_ket;
+    const int *K_bra, *K_ket;
+    int nket, row0, row1, same_class, shard, nshards, nshell, all_pass;
+    const double *DS;
+    const unsigned long long *dglob;
+    double tol;
+    uint2 *list;
+    unsigned long long *count, *primq, *cand;
+};
+
+__global__ void __launch_bounds__(256) screen_kernel(const ScreenArgs s)
+{
+    const int njb = (s.nket + 255) / 256;
+    const long long nblk = (long long)(s.row1 - s.row0) * njb;
+    const int lane = threadIdx.x & 31;
+    double dg4 = 0.0;
+    if (!s.all_pass) dg4 = 4.0 * __longlong_as_double((long long)*s.dglob);
+    unsigned long long my_cand = 0;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int i = s.row0 + (int)(blk / njb);
+        const int j = (int)(blk % njb) * 256 + threadIdx.x;
+        if (s.nshards > 1 && (i % s.nshards) != s.shard) continue;
+        const int jlim = s.same_class ? min(i + 1, s.nket) : s.nket;
+        if ((int)(blk % njb) * 256 >= jlim) continue;
+        bool pass = j < jlim;
+        unsigned long long kk = 0;
+        if (pass) {
+            ++my_cand;
+            if (!s.all_pass) {
+                const double qq = s.Qs_bra[i] * s.Qs_ket[j];
+                pass = !(qq * dg4 < s.tol);
+                if (pass) {
+                    const int2 ab = s.sh_bra[i], cd = s.sh_ket[j];
+                    const double *DS = s.DS;
+                    const int ns = s.nshell;
+                    double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
+                    dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
+                                           fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
+                    pass = !(qq * dmax < s.tol);
+                }
+            }
+            if (pass) kk = (unsigned long long)s.K_bra[i] * (unsigned long long)s.K_ket[j];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m) - 1;
+            // warp-level sum of primitive-quartet counts
+            unsigned long long ks = kk;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ks += __shfl_xor_sync(0xffffffffu, ks, o);
+            if (lane == leader) {
+                base = atomicAdd(s.count, (unsigned long long)__popc(m));
+                atomicAdd(s.primq, ks);
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) s.list[base + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)i, (unsigned)j);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_cand += __shfl_xor_sync(0xffffffffu, my_cand, o);
+    if (lane == 0 && my_cand) atomicAdd(s.cand, my_cand);
+}
+
+// scratch[entry][nfn] -> dense TwoE with all 8 images (cython/twoe.pyx:23-30)
+__global__ void scatter_dense_kernel(const uint2 *list, const unsigned long long *count, const PairHdr *braH,
+                                     const PairHdr *ketH, int la, int lb, int lc, int ld, const double *scratch,
+                                     int N, double *T)
+{
+    const int nb = ncart(lb), nc = ncart(lc), nd = ncart(ld);
+    const int nfn = ncart(la) * nb * nc * nd;
+    const unsigned long long total = (*count) * (unsigned long long)nfn;
+    const size_t n = (size_t)N;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = w / nfn;
+        int f = (int)(w % nfn);
+        const int d = f % nd; f /= nd;
+        const int c = f % nc; f /= nc;
+        const int bb = f % nb;
+        const int a = f / nb;
+        const uint2 ij = list[e];
+        const PairHdr bh = braH[ij.x], kh = ketH[ij.y];
+        const size_t i = bh.bfA + a, j = bh.bfB + bb, k = kh.bfA + c, l = kh.bfB + d;
+        const double v = scratch[w];
+        T[((i * n + j) * n + k) * n + l] = v;
+        T[((k * n + l) * n + i) * n + j] = v;
+        T[((j * n + i) * n + l) * n + k] = v;
+        T[((l * n + k) * n + j) * n + i] = v;
+        T[((j * n + i) * n + k) * n + l] = v;
+        T[((l * n + k) * n + i) * n + j] = v;
+        T[((i * n + j) * n + l) * n + k] = v;
+        T[((k * n + l) * n + j) * n + i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ERI entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int mmdb_eri_shell_quartets(mmdb_basis *b, int pc_bra, int pc_ket, int64_t n, const int32_t *bra_idx_dev,
+                                       const int32_t *ket_idx_dev, double *out_dev, int impl, void *stream)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    if (pc_bra < pc_ket || pc_bra >= MMDB_NCLASS_PAIR || pc_ket < 0)
+        return fail(MMDB_ERR_INVALID, "mmdb_eri_shell_quartets: need pc_bra >= pc_ket");
+    if (n == 0) return MMDB_OK;
+    CU(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CHK(ensure_list(b, (size_t)n));
+    zip_list_kernel<<<std::min<int64_t>((n + 255) / 256, 65535), 256, 0, st>>>(bra_idx_dev, ket_idx_dev, n, b->list_dev);
+    PairClass &B = b->pc[pc_bra], &K = b->pc[pc_ket];
+    EriArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+    a.list = b->list_dev; a.count_dev = nullptr; a.n = (unsigned long long)n; a.out = out_dev;
+    a.same_class = (pc_bra == pc_ket);
+    return launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, impl, st);
+}
+
+extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N2 = (size_t)b->nbf * b->nbf;
+    CU(cudaMemsetAsync(b->Q_dev, 0, N2 * sizeof(double), st));
+    CU(cudaMemsetAsync(b->SQ_dev, 0, N2 * sizeof(double), st));
+    for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
+        PairClass &P = b->pc[c];
+        if (P.npairs == 0) continue;
+        const int nab = ncart(P.la) * ncart(P.lb);
+        CHK(ensure_list(b, (size_t)P.npairs));
+        CHK(ensure_scratch(b, (size_t)P.npairs * nab * nab));
+        diag_list_kernel<<<(P.npairs + 255) / 256, 256, 0, st>>>(P.npairs, b->list_dev);
+        EriArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.braH = P.hdr_dev; a.braP = P.prim_dev; a.ketH = P.hdr_dev; a.ketP = P.prim_dev;
+        a.list = b->list_dev; a.n = (unsigned long long)P.npairs; a.out = b->scratch_dev; a.same_class = 1;
+        CHK(launch_eri(b, P.la, P.lb, P.la, P.lb, a, EPI_STORE, 0, st));
+        schwarz_extract_kernel<<<(P.npairs + 127) / 128, 128, 0, st>>>(P.hdr_dev, P.npairs, P.la, P.lb, b->scratch_dev,
+                                                                       b->nbf, b->Q_dev, b->SQ_dev, P.Qs_dev);
+    }
+    CU(cudaGetLastError());
+    if (Q_dev) CU(cudaMemcpyAsync(Q_dev, b->Q_dev, N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    b->have_schwarz = true;
+    return MMDB_OK;
+}
+
+static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
+                      bool all_pass, double tol, int slot, cudaStream_t st)
+{
+    ScreenArgs s;
+    s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
+    s.K_bra = B.K_dev; s.K_ket = K.K_dev;
+    s.nket = K.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
+    s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
+    s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = b->list_dev;
+    s.count = b->ctr_dev + 3 * slot; s.primq = b->ctr_dev + 3 * slot + 1; s.cand = b->ctr_dev + 3 * slot + 2;
+    const long long njb = (K.npairs + 255) / 256;
+    const long long nblk = (long long)(row1 - row0) * njb;
+    const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 64);
+    if (grid > 0) screen_kernel<<<grid, 256, 0, st>>>(s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MMDB_ERR_CUDA, std::string("screen kernel: ") + cudaGetErrorString(e));
+    return MMDB_OK;
+}
+
+static const size_t LIST_CAP = (size_t)1 << 27;      // entries per screening chunk (1 GiB of uint2)
+static const size_t SCRATCH_CAP = (size_t)1 << 27;   // doubles (1 GiB)
+
+extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = b->nbf;
+    CU(cudaMemsetAsync(TwoE_dev, 0, N * N * N * N * sizeof(double), st));
+    CU(cudaMemsetAsync(b->ctr_dev, 0, sizeof(unsigned long long) * b->nctr, st));
+    int slot = 0;
+    for (int cb = 0; cb < MMDB_NCLASS_PAIR; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            PairClass &B = b->pc[cb], &K = b->pc[ck];
+            if (B.npairs == 0 || K.npairs == 0) continue;
+            const size_t nfn = (size_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
+            size_t rows_per = std::max<size_t>(1, std::min(LIST_CAP, SCRATCH_CAP / nfn) / (size_t)K.npairs);
+            for (int row0 = 0; row0 < B.npairs; row0 += (int)rows_per) {
+                const int row1 = (int)std::min<size_t>(B.npairs, row0 + rows_per);
+                const size_t cap = (size_t)(row1 - row0) * K.npairs;
+                CHK(ensure_list(b, cap));
+                CHK(ensure_scratch(b, cap * nfn));
+                if (slot * 3 + 2 >= b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
+                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, st));
+                EriArgs a;
+                std::memset(&a, 0, sizeof(a));
+                a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+                a.list = b->list_dev; a.count_dev = b->ctr_dev + 3 * slot; a.out = b->scratch_dev;
+                a.same_class = (cb == ck);
+                CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, 0, st));
+                scatter_dense_kernel<<<b->nsm * 16, 256, 0, st>>>(b->list_dev, b->ctr_dev + 3 * slot, B.hdr_dev, K.hdr_dev,
+                                                                  B.la, B.lb, K.la, K.lb, b->scratch_dev, (int)N, TwoE_dev);
+                ++slot;
+            }
+        }
+    CU(cudaGetLastError());
+    return MMDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// direct Fock build
+// ------------------------------------------------------------------------------------------
+extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const double *dP_im_dev, double tol,
+                                double *G_re_dev, double *G_im_dev, int shard, int nshards, int flags,
+                                mmdb_fock_stats *stats, void *stream)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    if (!b->have_schwarz) return fail(MMDB_ERR_INVALID, "mmdb_fock_direct: call mmdb_schwarz first");
+    if (nshards < 1 || shard < 0 || shard >= nshards) return fail(MMDB_ERR_INVALID, "mmdb_fock_direct: bad shard");
+    if (dP_im_dev && !G_im_dev) return fail(MMDB_ERR_INVALID, "mmdb_fock_direct: imaginary density needs G_im");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = b->nbf;
+    const size_t N2 = (size_t)N * N;
+    dabs_kernel<<<b->nsm * 4, 256, 0, st>>>(dP_re_dev, dP_im_dev, N2, b->Dabs_dev);
+    CU(cudaMemsetAsync(b->dglob_dev, 0, sizeof(unsigned long long), st));
+    dshell_kernel<<<(b->nshell * b->nshell + 127) / 128, 128, 0, st>>>(b->Dabs_dev, N, b->sh_bf0_dev, b->sh_nf_dev,
+                                                                       b->nshell, b->DS_dev, b->dglob_dev);
+    CU(cudaMemsetAsync(b->ctr_dev, 0, sizeof(unsigned long long) * b->nctr, st));
+    struct Launch { int cb, ck, slot; cudaEvent_t e0, e1; };
+    std::vector<Launch> launches;
+    const bool timing = (flags & 1) != 0;
+    int slot = 0;
+    for (int cb = 0; cb < MMDB_NCLASS_PAIR; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            PairClass &B = b->pc[cb], &K = b->pc[ck];
+            if (B.npairs == 0 || K.npairs == 0) continue;
+            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)K.npairs);
+            for (int row0 = 0; row0 < B.npairs; row0 += (int)rows_per) {
+                const int row1 = (int)std::min<size_t>(B.npairs, row0 + rows_per);
+                CHK(ensure_list(b, (size_t)(row1 - row0) * K.npairs));
+                if (slot * 3 + 2 >= b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
+                Launch ln{cb, ck, slot, nullptr, nullptr};
+                if (timing) {
+                    CU(cudaEventCreate(&ln.e0));
+                    CU(cudaEventCreate(&ln.e1));
+                    CU(cudaEventRecord(ln.e0, st));
+                }
+                CHK(run_screen(b, B, K, cb == ck, row0, row1, shard, nshards, false, tol, slot, st));
+                EriArgs a;
+                std::memset(&a, 0, sizeof(a));
+                a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+                a.list = b->list_dev; a.count_dev = b->ctr_dev + 3 * slot; a.same_class = (cb == ck);
+                a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
+                a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
+                CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST, 0, st));
+                if (timing) CU(cudaEventRecord(ln.e1, st));
+                launches.push_back(ln);
+                ++slot;
+            }
+        }
+    if (stats) {
+        std::vector<unsigned long long> ctr(3 * (size_t)slot + 3, 0ull);
+        CU(cudaMemcpyAsync(ctr.data(), b->ctr_dev, sizeof(unsigned long long) * 3 * slot, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::memset(stats, 0, sizeof(*stats));
+        for (auto &ln : launches) {
+            const PairClass &B = b->pc[ln.cb], &K = b->pc[ln.ck];
+            const int64_t nq = (int64_t)ctr[3 * ln.slot], npq = (int64_t)ctr[3 * ln.slot + 1];
+            const int64_t nfn = (int64_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
+            stats->candidates += (int64_t)ctr[3 * ln.slot + 2];
+            stats->quartets += nq;
+            stats->prim_quartets += npq;
+            stats->fn_quartets += nq * nfn;
+            stats->model_flops += (double)npq * mmdb_class_flops(B.la, B.lb, K.la, K.lb) + 13.0 * (double)(nq * nfn);
+            stats->class_quartets[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += nq;
+            stats->class_prim_quartets[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += npq;
+            if (timing) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ln.e0, ln.e1);
+                stats->class_ms[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += ms;
+            }
+        }
+    } else if (timing) {
+        CU(cudaStreamSynchronize(st));
+    }
+    for (auto &ln : launches)
+        if (ln.e0) { cudaEventDestroy(ln.e0); cudaEventDestroy(ln.e1); }
+    CU(cudaGetLastError());
+    return MMDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer forms
+// ------------------------------------------------------------------------------------------
+extern "C" int mmdb_schwarz_host(mmdb_basis *b, double *Q_tri)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    CHK(mmdb_schwarz(b, nullptr, nullptr));
+    const int N = b->nbf;
+    std::vector<double> Q((size_t)N * N);
+    CU(cudaMemcpy(Q.data(), b->Q_dev, Q.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int p = 0; p < N; ++p)
+        for (int q = 0; q <= p; ++q) Q_tri[(size_t)p * (p + 1) / 2 + q] = Q[(size_t)p * N + q];
+    return MMDB_OK;
+}
+
+extern "C" int mmdb_eri_dense_host(mmdb_basis *b, double *TwoE_host)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(b->device));
+    const size_t N = b->nbf, n4 = N * N * N * N;
+    double *T = nullptr;
+    CU(cudaMalloc(&T, n4 * sizeof(double)));
+    int r = mmdb_eri_dense(b, T, nullptr);
+    if (r == MMDB_OK) {
+        cudaError_t e = cudaMemcpy(TwoE_host, T, n4 * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) r = fail(MMDB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(T);
+    return r;
+}
+
+__global__ void split_c128_diff_kernel(const double *P, const double *Pold, size_t n, double *re, double *im)
+{
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        re[x] = P[2 * x] - Pold[2 * x];
+        im[x] = P[2 * x + 1] - Pold[2 * x + 1];
+    }
+}
+__global__ void join_c128_kernel(const double *re, const double *im, size_t n, double *out)
+{
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        out[2 * x] = re[x];
+        out[2 * x + 1] = im ? im[x] : 0.0;
+    }
+}
+
+extern "C" int mmdb_formPT_host(mmdb_basis *b, const double *P_c128, const double *P_old_c128, double tol,
+                                double *G_c128, mmdb_fock_stats *stats)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(b->device));
+    const size_t N2 = (size_t)b->nbf * b->nbf;
+    double *buf = nullptr;   // [P | Pold | re | im | Gre | Gim] ; P/Pold/out interleaved (2*N2 each)
+    CU(cudaMalloc(&buf, sizeof(double) * N2 * 10));
+    double *dP = buf, *dPo = buf + 2 * N2, *re = buf + 4 * N2, *im = buf + 5 * N2, *Gre = buf + 6 * N2,
+           *Gim = buf + 7 * N2, *Gout = buf + 8 * N2;
+    int r = MMDB_OK;
+    bool has_im = false;
+    for (size_t x = 0; x < N2 && !has_im; ++x) has_im = (P_c128[2 * x + 1] != P_old_c128[2 * x + 1]);
+    cudaError_t e = cudaMemcpy(dP, P_c128, sizeof(double) * 2 * N2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dPo, P_old_c128, sizeof(double) * 2 * N2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(Gre, 0, sizeof(double) * 2 * N2);
+    if (e != cudaSuccess) {
+        cudaFree(buf);
+        return fail(MMDB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    split_c128_diff_kernel<<<b->nsm * 2, 256>>>(dP, dPo, N2, re, im);
+    r = mmdb_fock_direct(b, re, has_im ? im : nullptr, tol, Gre, has_im ? Gim : nullptr, 0, 1, 0, stats, nullptr);
+    if (r == MMDB_OK) {
+        join_c128_kernel<<<b->nsm * 2, 256>>>(Gre, has_im ? Gim : nullptr, N2, Gout);
+        e = cudaMemcpy(G_c128, Gout, sizeof(double) * 2 * N2, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) r = fail(MMDB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(buf);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// utilities: Boys probe, FP64 peak probe
+// ------------------------------------------------------------------------------------------
+__global__ void boys_probe_kernel(int mmax, int64_t n, const double *T, const double *tab, double *out)
+{
+    extern __shared__ double s_boys[];
+    for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = tab[x];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double F[BOYS_MAXL + 1];
+        boys_eval_rt(mmax, T[i], s_boys, F);
+        for (int m = 0; m <= mmax; ++m) out[i * (mmax + 1) + m] = F[m];
+    }
+}
+
+extern "C" int mmdb_boys_host(int device, int mmax, int64_t n, const double *T, double *out)
+{
+    if (mmax < 0 || mmax > BOYS_MAXL) return fail(MMDB_ERR_INVALID, "mmdb_boys_host: mmax out of range");
+    CU(cudaSetDevice(device));
+    std::vector<double> tab;
+    make_boys_table(mmax, tab);
+    double *dtab = nullptr, *dT = nullptr, *dout = nullptr;
+    CU(cudaMalloc(&dtab, tab.size() * sizeof(double)));
+    CU(cudaMalloc(&dT, n * sizeof(double)));
+    CU(cudaMalloc(&dout, n * (mmax + 1) * sizeof(double)));
+    CU(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dT, T, n * sizeof(double), cudaMemcpyHostToDevice));
+    boys_probe_kernel<<<148, 128, BOYS_ROWS * BOYS_STRIDE * sizeof(double)>>>(mmax, n, dT, dtab, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, n * (mmax + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dtab); cudaFree(dT); cudaFree(dout);
+    return MMDB_OK;
+}
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double c)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fma(x0, a, c); x1 = fma(x1, a, c); x2 = fma(x2, a, c); x3 = fma(x3, a, c);
+            x4 = fma(x4, a, c); x5 = fma(x5, a, c); x6 = fma(x6, a, c); x7 = fma(x7, a, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int mmdb_fp64_peak(int device, double *tflops, float *ms_out)
+{
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8, iters = 4096;
+    double *out = nullptr;
+    CU(cudaMalloc(&out, (size_t)grid * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(e0));
+        dfma_peak_kernel<<<grid, 256>>>(out, iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep >= 1) best = std::min(best, ms);
+    }
+    const double flops = 2.0 * 8 * 16 * (double)iters * grid * 256;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    cudaFree(out);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return MMDB_OK;
+}

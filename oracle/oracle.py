@@ -1,0 +1,157 @@
+"""ctypes front-end of oracle/libmdoracle.so (md_oracle.c) — TEST INFRASTRUCTURE ONLY.
+
+Parity status: pinned (see md_oracle.c header).  Functions mirror the reference's names:
+boys/E/R (cython/util.pxi), ERI/doERIs (cython/twoe.pyx), formPT (cython/fock.pyx),
+jk_incore (mmd/scf.py:97-98), normalize (cython/basis.pxi:87-120).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libmdoracle.so")
+    src = os.path.join(_HERE, "md_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libmdoracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        basis = [_dp, _lp, _lp, _lp, _dp, _dp, _dp]
+        L.mdo_boys.restype = C.c_double
+        L.mdo_boys.argtypes = [C.c_double, C.c_double]
+        L.mdo_E.restype = C.c_double
+        L.mdo_E.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.mdo_R.restype = C.c_double
+        L.mdo_R.argtypes = [C.c_int] * 4 + [C.c_double] * 5
+        L.mdo_electron_repulsion.restype = C.c_double
+        L.mdo_electron_repulsion.argtypes = [C.c_double, _lp, _dp] * 4
+        L.mdo_normalize.restype = None
+        L.mdo_normalize.argtypes = [_lp, C.c_long, _dp, _dp, _dp]
+        L.mdo_ERI.restype = C.c_double
+        L.mdo_ERI.argtypes = [C.c_long] + basis + [C.c_long] * 4
+        L.mdo_ERI_batch.restype = None
+        L.mdo_ERI_batch.argtypes = [C.c_long] + basis + [C.c_long, _lp, _dp]
+        L.mdo_doERIs.restype = None
+        L.mdo_doERIs.argtypes = [C.c_long, _dp] + basis
+        L.mdo_schwarz.restype = None
+        L.mdo_schwarz.argtypes = [C.c_long, _dp] + basis
+        L.mdo_formPT.restype = None
+        L.mdo_formPT.argtypes = [C.c_long, _dp, _dp, _dp, C.c_double, _dp, C.POINTER(C.c_long)] + basis
+        L.mdo_jk_incore.restype = None
+        L.mdo_jk_incore.argtypes = [C.c_long, _dp, _dp, _dp, _dp]
+        _LIB = L
+    return _LIB
+
+
+def boys(m, T):
+    return lib().mdo_boys(float(m), float(T))
+
+
+def E(i, j, t, Qx, a, b):
+    return lib().mdo_E(i, j, t, Qx, a, b)
+
+
+def R(t, u, v, n, p, PCx, PCy, PCz, RPC):
+    return lib().mdo_R(t, u, v, n, p, PCx, PCy, PCz, RPC)
+
+
+def normalize(shell, exps, coefs):
+    """-> (normalised coefs, primitive norms), cython/basis.pxi:87-120."""
+    lmn = np.ascontiguousarray(shell, dtype=np.int64)
+    e = np.ascontiguousarray(exps, dtype=np.float64)
+    c = np.array(coefs, dtype=np.float64)
+    n = np.zeros_like(e)
+    lib().mdo_normalize(lmn, len(e), e, c, n)
+    return c, n
+
+
+class FlatBasis(object):
+    """Flat-array image of a list of reference-style Basis objects (duck-typed:
+    .origin .shell .num_exps .exps .coefs(normalised) .norm)."""
+
+    def __init__(self, bfs):
+        self.nbf = len(bfs)
+        self.origin = np.ascontiguousarray([np.asarray(b.origin, dtype=np.float64) for b in bfs]).reshape(-1)
+        self.shell = np.ascontiguousarray([np.asarray(b.shell, dtype=np.int64) for b in bfs]).reshape(-1)
+        self.nprim = np.ascontiguousarray([int(b.num_exps) for b in bfs], dtype=np.int64)
+        self.off = np.zeros(self.nbf, dtype=np.int64)
+        self.off[1:] = np.cumsum(self.nprim)[:-1]
+        self.exps = np.ascontiguousarray(np.concatenate([np.asarray(b.exps, dtype=np.float64) for b in bfs]))
+        self.coefs = np.ascontiguousarray(np.concatenate([np.asarray(b.coefs, dtype=np.float64) for b in bfs]))
+        self.norm = np.ascontiguousarray(np.concatenate([np.asarray(b.norm, dtype=np.float64) for b in bfs]))
+
+    def args(self):
+        return (self.origin, self.shell, self.nprim, self.off, self.exps, self.coefs, self.norm)
+
+
+def _fb(bfs):
+    return bfs if isinstance(bfs, FlatBasis) else FlatBasis(bfs)
+
+
+def ERI(a, b, c, d):
+    fb = FlatBasis([a, b, c, d])
+    return lib().mdo_ERI(4, *fb.args(), 0, 1, 2, 3)
+
+
+def ERI_batch(bfs, idx):
+    fb = _fb(bfs)
+    idx = np.ascontiguousarray(idx, dtype=np.int64).reshape(-1, 4)
+    out = np.zeros(len(idx))
+    lib().mdo_ERI_batch(fb.nbf, *fb.args(), len(idx), idx.reshape(-1), out)
+    return out
+
+
+def doERIs(N, TwoE, bfs):
+    fb = _fb(bfs)
+    assert TwoE.shape == (N, N, N, N) and TwoE.flags.c_contiguous and TwoE.dtype == np.float64
+    lib().mdo_doERIs(N, TwoE.reshape(-1), *fb.args())
+    return TwoE
+
+
+def schwarz(bfs):
+    fb = _fb(bfs)
+    N = fb.nbf
+    out = np.zeros(N * (N + 1) // 2)
+    lib().mdo_schwarz(N, out, *fb.args())
+    return out
+
+
+def formPT(P, P_old, bfs, nbasis, screen, tol, return_count=False):
+    """screen: dict {pq: value} like the reference, or a flat array of N(N+1)/2."""
+    fb = _fb(bfs)
+    N = int(nbasis)
+    if isinstance(screen, dict):
+        scr = np.array([screen[k] for k in range(N * (N + 1) // 2)], dtype=np.float64)
+    else:
+        scr = np.ascontiguousarray(screen, dtype=np.float64)
+    Pc = np.ascontiguousarray(P, dtype=np.complex128)
+    Po = np.ascontiguousarray(P_old, dtype=np.complex128)
+    G = np.zeros((N, N), dtype=np.complex128)
+    cnt = C.c_long(0)
+    lib().mdo_formPT(N, Pc.view(np.float64).reshape(-1), Po.view(np.float64).reshape(-1), scr, float(tol),
+                     G.view(np.float64).reshape(-1), C.byref(cnt), *fb.args())
+    return (G, cnt.value) if return_count else G
+
+
+def jk_incore(TwoE, P):
+    N = TwoE.shape[0]
+    T = np.ascontiguousarray(TwoE, dtype=np.float64)
+    Pc = np.ascontiguousarray(P, dtype=np.complex128)
+    J = np.zeros((N, N), dtype=np.complex128)
+    K = np.zeros((N, N), dtype=np.complex128)
+    lib().mdo_jk_incore(N, T.reshape(-1), Pc.view(np.float64).reshape(-1), J.view(np.float64).reshape(-1),
+                        K.view(np.float64).reshape(-1))
+    return J, K
