@@ -79,6 +79,10 @@ int mmdb_eri_shell_quartets(mmdb_basis *b, int pc_bra, int pc_ket, int64_t n, co
  * sqrt(Q) and the per-shell-pair maxima inside the handle for mmdb_fock_direct. */
 int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream);
 
+/* Install a caller-supplied Schwarz table instead (the reference lets the caller pass any `screen`
+ * dict to formPT): Q_tri[p(p+1)/2+q] for p >= q, host memory. */
+int mmdb_set_schwarz_host(mmdb_basis *b, const double *Q_tri);
+
 /* Dense (N,N,N,N) row-major tensor, all 8 permutational images written (cython/twoe.pyx:12-31).
  * TwoE_dev must hold N^4 doubles; every element is written (no pre-zeroing needed). */
 int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream);

@@ -706,6 +706,49 @@ extern "C" int mmdb_schwarz_host(mmdb_basis *b, double *Q_tri)
     return MMDB_OK;
 }
 
+// Qs[i] = max over the pair's function pairs of sqrt|Q|; SQ = sqrt(Q) from a caller-supplied table
+__global__ void schwarz_from_Q_kernel(const PairHdr *hdr, int npairs, int la, int lb, int N, const double *Q,
+                                      double *SQ, double *Qs)
+{
+    const int na = ncart(la), nb = ncart(lb);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const PairHdr h = hdr[i];
+        double qmax = 0.0;
+        for (int a = 0; a < na; ++a)
+            for (int c = 0; c < nb; ++c) {
+                const int p = h.bfA + a, q = h.bfB + c;
+                const double v = Q[(size_t)p * N + q];
+                const double s = sqrt(v);
+                SQ[(size_t)p * N + q] = s;
+                SQ[(size_t)q * N + p] = s;
+                qmax = fmax(qmax, sqrt(fabs(v)));
+            }
+        Qs[i] = qmax;
+    }
+}
+
+extern "C" int mmdb_set_schwarz_host(mmdb_basis *b, const double *Q_tri)
+{
+    if (!b) return fail(MMDB_ERR_INVALID, "null handle");
+    CU(cudaSetDevice(b->device));
+    const int N = b->nbf;
+    std::vector<double> Q((size_t)N * N);
+    for (int p = 0; p < N; ++p)
+        for (int q = 0; q <= p; ++q) Q[(size_t)p * N + q] = Q[(size_t)q * N + p] = Q_tri[(size_t)p * (p + 1) / 2 + q];
+    CU(cudaMemcpy(b->Q_dev, Q.data(), Q.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemset(b->SQ_dev, 0, Q.size() * sizeof(double)));
+    for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
+        PairClass &P = b->pc[c];
+        if (P.npairs == 0) continue;
+        schwarz_from_Q_kernel<<<(P.npairs + 127) / 128, 128>>>(P.hdr_dev, P.npairs, P.la, P.lb, N, b->Q_dev, b->SQ_dev,
+                                                                P.Qs_dev);
+    }
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    b->have_schwarz = true;
+    return MMDB_OK;
+}
+
 extern "C" int mmdb_eri_dense_host(mmdb_basis *b, double *TwoE_host)
 {
     if (!b) return fail(MMDB_ERR_INVALID, "null handle");

@@ -1,0 +1,305 @@
+"""Engine: one GPU's two-electron engine for one list of basis functions.
+
+Python owns every user-visible buffer (numpy on the host, torch tensors on the device — torch is
+only the device-buffer carrier and the NCCL plumbing); libmmdb200.so owns the shell-pair tables
+behind an opaque handle.  All arithmetic happens in the CUDA kernels of csrc/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import lib as L
+from .shells import ShellTable
+
+_PRIM_CUT = float(os.environ.get("MMDB_PRIM_CUT", "1e-20"))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class SchwarzTable(dict):
+    """The reference's `screen` dict (mmd/molecule.py:95-99): key p(p+1)//2+q -> (pq|pq).
+    Remembers which engine already holds it on the device so formPT need not upload it again."""
+    engine = None
+    flat = None
+
+
+class Engine(object):
+    def __init__(self, bfs, device=None, prim_cut=None):
+        L.require_gpu()
+        torch = _torch()
+        self.lib = L.load()
+        self.table = ShellTable(bfs)
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        t = self.table
+        h = C.c_void_p()
+        L.check(self.lib.mmdb_basis_create(self.device, t.nshell, L.ptr(t.am), L.ptr(t.nprim), L.ptr(t.poff),
+                                           L.ptr(t.centre), L.ptr(t.exps), L.ptr(t.coefs), L.ptr(t.bf0),
+                                           _PRIM_CUT if prim_cut is None else float(prim_cut), C.byref(h)))
+        self.h = h
+        self.N = t.nuser
+        self.Ndev = t.ndev
+        npairs = np.zeros(L.NCLASS_PAIR, dtype=np.int64)
+        nprimpairs = np.zeros(L.NCLASS_PAIR, dtype=np.int64)
+        L.check(self.lib.mmdb_basis_pair_counts(self.h, L.ptr(npairs), L.ptr(nprimpairs)))
+        self.npairs, self.nprimpairs = npairs, nprimpairs
+        # (shell A, shell B) -> (pair class, index in class, flipped?)
+        ns = t.nshell
+        self.pair_class = np.full((ns, ns), -1, dtype=np.int64)
+        self.pair_index = np.full((ns, ns), -1, dtype=np.int64)
+        self.pair_flip = np.zeros((ns, ns), dtype=bool)
+        for pc in range(L.NCLASS_PAIR):
+            n = int(npairs[pc])
+            if n == 0:
+                continue
+            sa = np.zeros(n, dtype=np.int32)
+            sb = np.zeros(n, dtype=np.int32)
+            L.check(self.lib.mmdb_basis_pair_shells(self.h, pc, L.ptr(sa), L.ptr(sb)))
+            idx = np.arange(n)
+            self.pair_class[sa, sb] = pc
+            self.pair_index[sa, sb] = idx
+            self.pair_class[sb, sa] = pc
+            self.pair_index[sb, sa] = idx
+            self.pair_flip[sb, sa] = True
+            self.pair_flip[sa, sb] = False
+        self._schwarz = None
+        self._schwarz_owner_id = None
+        self.TwoE_dev = None
+        self.last_stats = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and self.h.value:
+                self.lib.mmdb_basis_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.tdev).cuda_stream)
+
+    def _ncart(self, l):
+        return (l + 1) * (l + 2) // 2
+
+    # ---- individual contracted integrals (cython/twoe.pyx:36-50 ERI) -------------------------
+    def eri_quartets(self, idx, impl=0):
+        """(ij|kl) for user function quartets idx[n,4]."""
+        torch = _torch()
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1, 4)
+        t = self.table
+        d = t.user2dev[idx]
+        sh = t.fn_shell[d]
+        cp = t.fn_comp[d]
+        out = np.zeros(len(idx), dtype=np.float64)
+        A, B, Cc, D = sh[:, 0], sh[:, 1], sh[:, 2], sh[:, 3]
+        pcb, pib, flb = self.pair_class[A, B], self.pair_index[A, B], self.pair_flip[A, B]
+        pck, pik, flk = self.pair_class[Cc, D], self.pair_index[Cc, D], self.pair_flip[Cc, D]
+        a = np.where(flb, cp[:, 1], cp[:, 0])
+        b = np.where(flb, cp[:, 0], cp[:, 1])
+        c = np.where(flk, cp[:, 3], cp[:, 2])
+        dd = np.where(flk, cp[:, 2], cp[:, 3])
+        swap = pcb < pck
+        pcb2, pck2 = np.where(swap, pck, pcb), np.where(swap, pcb, pck)
+        pib2, pik2 = np.where(swap, pik, pib), np.where(swap, pib, pik)
+        a2, b2 = np.where(swap, c, a), np.where(swap, dd, b)
+        c2, d2 = np.where(swap, a, c), np.where(swap, b, dd)
+        alive = (pcb >= 0) & (pck >= 0)   # pairs dropped by the primitive cut are exactly negligible
+        with torch.cuda.device(self.tdev):
+            for cb in range(L.NCLASS_PAIR):
+                for ck in range(cb + 1):
+                    sel = np.nonzero(alive & (pcb2 == cb) & (pck2 == ck))[0]
+                    if len(sel) == 0:
+                        continue
+                    (la, lb), (lc, ld) = L.PAIR_CLASSES[cb], L.PAIR_CLASSES[ck]
+                    nb, nc, nd = self._ncart(lb), self._ncart(lc), self._ncart(ld)
+                    nfn = self._ncart(la) * nb * nc * nd
+                    # unique shell quartets among the requested function quartets
+                    key = pib2[sel] * (int(self.npairs[ck]) + 1) + pik2[sel]
+                    uk, inv = np.unique(key, return_inverse=True)
+                    bi = torch.from_numpy((uk // (int(self.npairs[ck]) + 1)).astype(np.int32)).to(self.tdev)
+                    ki = torch.from_numpy((uk % (int(self.npairs[ck]) + 1)).astype(np.int32)).to(self.tdev)
+                    buf = torch.empty(len(uk) * nfn, dtype=torch.float64, device=self.tdev)
+                    L.check(self.lib.mmdb_eri_shell_quartets(self.h, cb, ck, len(uk), L.ptr(bi), L.ptr(ki), L.ptr(buf),
+                                                             int(impl), self._stream()))
+                    vals = buf.cpu().numpy().reshape(len(uk), nfn)
+                    f = ((a2[sel] * nb + b2[sel]) * nc + c2[sel]) * nd + d2[sel]
+                    out[sel] = vals[inv, f]
+        return out
+
+    # ---- Schwarz table (mmd/molecule.py:95-99) -------------------------------------------------
+    def schwarz(self):
+        torch = _torch()
+        with torch.cuda.device(self.tdev):
+            Q = torch.empty((self.Ndev, self.Ndev), dtype=torch.float64, device=self.tdev)
+            L.check(self.lib.mmdb_schwarz(self.h, L.ptr(Q), self._stream()))
+            Qh = self.table.to_user_matrix(Q.cpu().numpy())
+        N = self.N
+        p, q = np.tril_indices(N)
+        flat = np.ascontiguousarray(Qh[p, q])        # order p(p+1)/2+q
+        tab = SchwarzTable(zip(range(len(flat)), flat.tolist()))
+        tab.engine = self
+        tab.flat = flat
+        self._schwarz = tab
+        self._schwarz_owner_id = id(tab)
+        return tab
+
+    def _install_screen(self, screen):
+        """Make sure the device holds the caller's `screen` (dict keyed p(p+1)//2+q, or flat array)."""
+        if screen is None:
+            if self._schwarz is None:
+                self.schwarz()
+            return
+        if isinstance(screen, SchwarzTable) and screen.engine is self and self._schwarz_owner_id == id(screen):
+            return
+        N = self.N
+        ntri = N * (N + 1) // 2
+        if isinstance(screen, dict):
+            flat = np.fromiter((screen[k] for k in range(ntri)), dtype=np.float64, count=ntri)
+        else:
+            flat = np.ascontiguousarray(screen, dtype=np.float64)
+        if not self.table.identity:
+            Qu = np.zeros((N, N))
+            p, q = np.tril_indices(N)
+            Qu[p, q] = flat
+            Qu[q, p] = flat
+            Qd = self.table.to_dev_matrix(Qu)
+            p, q = np.tril_indices(self.Ndev)
+            flat = np.ascontiguousarray(Qd[p, q])
+        L.check(self.lib.mmdb_set_schwarz_host(self.h, L.ptr(flat)))
+        self._schwarz_owner_id = id(screen)
+
+    # ---- dense tensor (cython/twoe.pyx:12-31 doERIs) -------------------------------------------
+    def dense(self, keep_device=True):
+        torch = _torch()
+        n = self.Ndev
+        with torch.cuda.device(self.tdev):
+            T = torch.empty((n, n, n, n), dtype=torch.float64, device=self.tdev)
+            L.check(self.lib.mmdb_eri_dense(self.h, L.ptr(T), self._stream()))
+            host = T.cpu().numpy()
+        if self.table.identity:
+            if keep_device:
+                self.TwoE_dev = T
+            return host
+        host = self.table.to_user_tensor4(host)
+        if keep_device:
+            self.TwoE_dev = torch.from_numpy(host).to(self.tdev)
+        return host
+
+    # ---- in-core J/K (mmd/scf.py:97-98) ----------------------------------------------------------
+    def jk_incore(self, P, TwoE=None):
+        """J, K (complex128 (N,N)) from the dense tensor; P complex or real (N,N), user order."""
+        torch = _torch()
+        N = self.N
+        with torch.cuda.device(self.tdev):
+            if TwoE is not None:
+                T = TwoE if not isinstance(TwoE, np.ndarray) else torch.from_numpy(np.ascontiguousarray(TwoE)).to(self.tdev)
+            else:
+                if self.TwoE_dev is None:
+                    raise L.MMDBError("jk_incore: no device-resident TwoE (call dense() first)")
+                T = self.TwoE_dev
+            P = np.asarray(P)
+            Pre = torch.from_numpy(np.ascontiguousarray(P.real, dtype=np.float64)).to(self.tdev)
+            cplx = np.iscomplexobj(P) and bool(np.any(P.imag != 0.0))
+            Pim = torch.from_numpy(np.ascontiguousarray(P.imag, dtype=np.float64)).to(self.tdev) if cplx else None
+            out = torch.empty((4, N, N), dtype=torch.float64, device=self.tdev)
+            L.check(self.lib.mmdb_jk_incore(self.device, L.ptr(T), N, L.ptr(Pre), L.ptr(Pim), L.ptr(out[0]),
+                                            L.ptr(out[1]) if cplx else None, L.ptr(out[2]),
+                                            L.ptr(out[3]) if cplx else None, self._stream()))
+            o = out.cpu().numpy()
+        J = o[0].astype(np.complex128)
+        K = o[2].astype(np.complex128)
+        if cplx:
+            J += 1j * o[1]
+            K += 1j * o[3]
+        return J, K
+
+    # ---- direct Fock build (cython/fock.pyx:13-87 formPT) ----------------------------------------
+    def formPT(self, P, P_old, screen=None, tol=1e-12, want_stats=True, flags=0):
+        """Un-symmetrised G (complex128, user order).  Shards over torch.distributed ranks when a
+        process group with world_size > 1 is initialised (one process per GPU) and sums the partial
+        G matrices with one all-reduce (NCCL over NVLink)."""
+        torch = _torch()
+        self._install_screen(screen)
+        dP = np.asarray(P) - np.asarray(P_old)
+        dPd = self.table.to_dev_matrix(dP)
+        n = self.Ndev
+        cplx = np.iscomplexobj(dPd) and bool(np.any(dPd.imag != 0.0))
+        rank, world = 0, 1
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            rank, world = dist.get_rank(), dist.get_world_size()
+        with torch.cuda.device(self.tdev):
+            re = torch.from_numpy(np.ascontiguousarray(dPd.real, dtype=np.float64)).to(self.tdev)
+            im = torch.from_numpy(np.ascontiguousarray(dPd.imag, dtype=np.float64)).to(self.tdev) if cplx else None
+            G = torch.zeros((2 if cplx else 1, n, n), dtype=torch.float64, device=self.tdev)
+            stats = L.FockStats() if want_stats else None
+            L.check(self.lib.mmdb_fock_direct(self.h, L.ptr(re), L.ptr(im), float(tol), L.ptr(G[0]),
+                                              L.ptr(G[1]) if cplx else None, rank, world, int(flags),
+                                              C.byref(stats) if want_stats else None, self._stream()))
+            if world > 1:
+                dist.all_reduce(G)
+            g = G.cpu().numpy()
+        self.last_stats = stats.as_dict() if want_stats else None
+        out = g[0].astype(np.complex128)
+        if cplx:
+            out += 1j * g[1]
+        return self.table.to_user_matrix(out)
+
+    # ---- one-electron integrals (cython/onee.pyx) ------------------------------------------------
+    def onee(self, charges, coords, origin):
+        Z = np.ascontiguousarray(charges, dtype=np.float64)
+        xyz = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1)
+        org = np.ascontiguousarray(origin, dtype=np.float64)
+        n = self.Ndev
+        S = np.zeros((n, n)); T = np.zeros((n, n)); V = np.zeros((n, n))
+        M = np.zeros((3, n, n)); Lm = np.zeros((3, n, n))
+        L.check(self.lib.mmdb_onee_host(self.h, len(Z), L.ptr(Z), L.ptr(xyz), L.ptr(org), L.ptr(S), L.ptr(T), L.ptr(V),
+                                        L.ptr(M), L.ptr(Lm)))
+        if self.table.identity:
+            return S, T, V, M, Lm
+        u = self.table.user2dev
+        ix = np.ix_(u, u)
+        return (np.ascontiguousarray(S[ix]), np.ascontiguousarray(T[ix]), np.ascontiguousarray(V[ix]),
+                np.ascontiguousarray(M[:, u][:, :, u]), np.ascontiguousarray(Lm[:, u][:, :, u]))
+
+
+# ---- engine cache keyed by the identity of the Basis objects in the list ----------------------
+_CACHE = {}
+
+
+def engine_for(bfs):
+    key = tuple(id(b) for b in bfs)
+    hit = _CACHE.get(key)
+    if hit is not None:
+        return hit
+    if len(_CACHE) > 8:
+        _CACHE.clear()
+    eng = Engine(bfs)
+    eng._keepalive = list(bfs)
+    _CACHE[key] = eng
+    return eng
+
+
+def boys(n, T):
+    """F_n(T) from the device Boys routine (test hook, mirrors onee._boys of the reference)."""
+    L.require_gpu()
+    Ts = np.ascontiguousarray(np.atleast_1d(np.asarray(T, dtype=np.float64)))
+    n = int(n)
+    out = np.zeros((len(Ts), n + 1))
+    L.check(L.load().mmdb_boys_host(_torch().cuda.current_device(), n, len(Ts), L.ptr(Ts), L.ptr(out)))
+    return out
+
+
+def fp64_peak(device=0):
+    L.require_gpu()
+    tf = C.c_double(0.0)
+    ms = C.c_float(0.0)
+    L.check(L.load().mmdb_fp64_peak(int(device), C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value

@@ -1,0 +1,155 @@
+"""Molecule: geometry + basis -> basis functions -> integrals.  Public behaviour follows the
+reference's mmd/molecule.py (same constructor, attributes and method names); the integral work is
+done by the B200 engine:
+
+    build(direct=False)  ->  one-electron matrices (device kernel), then either the dense TwoE
+                             tensor (doERIs) or the Schwarz table for the direct Fock build.
+"""
+import itertools
+import os
+import sys
+
+import numpy as np
+from scipy.linalg import fractional_matrix_power
+
+from mmd._b200 import basisio
+from mmd._b200.engine import engine_for
+from mmd.integrals.twoe import Basis, doERIs
+from mmd.scf import SCF
+
+BOHR_PER_ANGSTROM = 1.0 / 0.52917721092      # mmd/molecule.py:224
+AMU_TO_AU = 1822.8885
+
+# isotope-averaged masses as tabulated by the reference (index = atomic number; the value for
+# oxygen is the reference's, kept for drop-in behaviour)
+_MASSES = [0.0, 1.008, 4.003, 6.941, 9.012, 10.812, 12.011, 14.007, 5.999, 18.998, 20.180, 22.990,
+           24.305, 26.982, 28.086, 30.974, 32.066, 35.453, 39.948]
+
+_SHELL_COMPONENTS = {
+    "S": [(0, 0, 0)],
+    "P": [(1, 0, 0), (0, 1, 0), (0, 0, 1)],
+    "D": [(2, 0, 0), (1, 1, 0), (1, 0, 1), (0, 2, 0), (0, 1, 1), (0, 0, 2)],
+    "F": [(3, 0, 0), (2, 1, 0), (2, 0, 1), (1, 2, 0), (1, 1, 1), (1, 0, 2), (0, 3, 0), (0, 2, 1), (0, 1, 2), (0, 0, 3)],
+}
+
+
+class Atom(object):
+    def __init__(self, charge, mass, origin=np.zeros(3)):
+        self.charge = charge
+        self.mass = mass
+        self.origin = origin
+        self.forces = np.zeros(3)
+        self.saved_forces = np.zeros(3)
+        self.velocities = np.zeros(3)
+
+
+class Molecule(SCF):
+    """Molecule(geometry, basis='sto-3g'); geometry = 'charge mult' line then 'Sym x y z' (Angstrom)."""
+
+    def __init__(self, geometry, basis="sto-3g"):
+        self.charge, self.multiplicity, self.atoms = self.read_molecule(geometry)
+        self.nelec = sum(atom.charge for atom in self.atoms) - self.charge
+        self.nocc = self.nelec // 2
+        self.is_built = False
+        self.geometry_input = geometry
+        self.basis_name = str(basis)
+        self.basis_data = self.getBasis(basis)
+        self.formBasis()
+
+    # ---- parsing -----------------------------------------------------------------------------
+    def sym2num(self, sym):
+        return basisio.atomic_number(sym)
+
+    def getBasis(self, filename):
+        """{atomic number: [(momentum, [(exp, coef), ...]), ...]}; accepts a basis name or a path."""
+        return basisio.load_basis(filename, os.path.join(os.path.dirname(os.path.abspath(__file__)), "basis"))
+
+    def momentum2shell(self, momentum):
+        return _SHELL_COMPONENTS[str(momentum)]
+
+    def read_molecule(self, geometry):
+        lines = [ln for ln in geometry.split("\n") if ln]
+        head = lines[0].split()
+        assert len(head) == 2
+        charge, multiplicity = int(head[0]), int(head[1])
+        atoms = []
+        for ln in lines[1:]:
+            tok = ln.split()
+            if len(tok) == 0:
+                break
+            assert len(tok) == 4
+            z = self.sym2num(tok[0])
+            xyz = np.asarray([float(tok[1]) / 0.52917721092, float(tok[2]) / 0.52917721092,
+                              float(tok[3]) / 0.52917721092])
+            atoms.append(Atom(charge=z, mass=_MASSES[z] * AMU_TO_AU, origin=xyz))
+        return charge, multiplicity, atoms
+
+    # ---- basis functions ---------------------------------------------------------------------
+    def formBasis(self):
+        """self.bfs: atoms in input order -> shells in file order -> Cartesian components."""
+        self.bfs = []
+        for atom in self.atoms:
+            atom_first = len(self.bfs)
+            for momentum, prims in self.basis_data[atom.charge]:
+                exps = np.asarray([e for e, _ in prims])
+                coefs = np.asarray([c for _, c in prims])
+                for lmn in self.momentum2shell(momentum):
+                    self.bfs.append(Basis(np.asarray(atom.origin), np.asarray(lmn), len(exps), exps, coefs))
+            atom._bf_range = (atom_first, len(self.bfs))
+        self.nbasis = len(self.bfs)
+        for atom in self.atoms:            # masks used by geometric-derivative code
+            atom.mask = np.zeros(self.nbasis)
+            atom.mask[atom._bf_range[0]:atom._bf_range[1]] = 1.0
+        zsum = float(sum(atom.charge for atom in self.atoms))
+        self.center_of_charge = np.asarray(
+            [sum(atom.charge * atom.origin[k] for atom in self.atoms) for k in range(3)]) * (1.0 / zsum)
+
+    # ---- integrals ---------------------------------------------------------------------------
+    @property
+    def engine(self):
+        return engine_for(self.bfs)
+
+    def build(self, direct=False):
+        self.one_electron_integrals()
+        if direct:
+            self.screen = self.engine.schwarz()     # dict keyed p(p+1)//2+q, like the reference
+        else:
+            self.two_electron_integrals()
+        self.is_built = True
+
+    def one_electron_integrals(self):
+        Z = np.asarray([atom.charge for atom in self.atoms], dtype=float)
+        xyz = np.asarray([atom.origin for atom in self.atoms], dtype=float)
+        self.S, self.T, self.V, self.M, self.L = self.engine.onee(Z, xyz, self.center_of_charge)
+        self.mu = np.zeros(3, dtype="complex")
+        self.nuc_energy = 0.0
+        for a, b in itertools.combinations(self.atoms, 2):
+            self.nuc_energy += a.charge * b.charge / np.linalg.norm(a.origin - b.origin)
+        self.Core = self.T + self.V
+        self.X = fractional_matrix_power(self.S, -0.5)
+        self.U = fractional_matrix_power(self.S, 0.5)
+
+    def two_electron_integrals(self):
+        N = self.nbasis
+        self.TwoE = np.zeros((N, N, N, N))
+        self.TwoE = np.asarray(doERIs(N, self.TwoE, self.bfs))
+
+    def save_integrals(self, folder=None):
+        """Crawford-format text dump (enuc, nbf, nelec, s, t, v, eri with 1-based indices)."""
+        if folder is None:
+            sys.exit("Please provide a folder to save the integrals.")
+        if not self.is_built:
+            self.build()
+        os.makedirs(folder, exist_ok=True)
+        np.savetxt(folder + "/enuc.dat", np.asarray(self.nuc_energy).reshape(1,))
+        np.savetxt(folder + "/nbf.dat", np.asarray(self.nbasis, dtype=int).reshape(1,), fmt="%d")
+        np.savetxt(folder + "/nelec.dat", np.asarray(self.nelec, dtype=int).reshape(1,), fmt="%d")
+        np.savetxt(folder + "/s.dat", self.S)
+        np.savetxt(folder + "/t.dat", self.T)
+        np.savetxt(folder + "/v.dat", self.V)
+        n = self.nbasis
+        with open(folder + "/eri.dat", "w") as f:
+            for i, j, k, l in itertools.product(range(n), repeat=4):
+                print(i + 1, j + 1, k + 1, l + 1, self.TwoE[i, j, k, l], file=f)
+        with open(folder + "/geometry.txt", "w") as f:
+            print(self.geometry_input, file=f)

@@ -1,0 +1,55 @@
+"""Post-SCF: AO->MO transformation and MP2 on top of a converged in-core RHF (consumers of the
+dense mol.TwoE tensor the B200 engine produced).  Mirrors PostSCF(mol).MP2() of the reference's
+mmd/postscf.py:15-72.  Determinant-based methods (CIS/TDHF/CISD/FCI) are outside the hot path this
+package accelerates and are not provided."""
+import sys
+from itertools import product
+
+import numpy as np
+
+
+class PostSCF(object):
+    def __init__(self, mol):
+        self.mol = mol
+        if not self.mol.is_converged:
+            sys.exit("SCF not converged, skipping Post-SCF")
+        if not hasattr(self.mol, "TwoE"):
+            sys.exit("Post-SCF needs the in-core tensor: run RHF(direct=False)")
+        self.ao2mo()
+
+    def ao2mo(self):
+        """(pq|rs) -> MO basis by four quarter transformations; mol.single_bar[P,Q,R,S]."""
+        C = self.mol.C
+        t = np.einsum("pqrs,sS->pqrS", self.mol.TwoE, C, optimize=True)
+        t = np.einsum("pqrS,rR->pqRS", t, C, optimize=True)
+        t = np.einsum("pqRS,qQ->pQRS", t, C, optimize=True)
+        self.mol.single_bar = np.einsum("pQRS,pP->PQRS", t, C, optimize=True)
+        self.mol.norb = self.mol.nbasis * 2
+        self._spin = np.eye(2)
+        # spin-orbital quantities are O((2N)^4) and only needed for spin_orbital=True: built lazily
+        self.mol.fs = np.kron(np.diag(self.mol.MO), self._spin)
+        self.mol.Hp = np.kron(np.einsum("uj,vi,uv", C, C, self.mol.Core).real, self._spin)
+
+    def _ensure_double_bar(self):
+        if getattr(self.mol, "double_bar", None) is None or not hasattr(self.mol, "double_bar"):
+            block = np.kron(np.kron(self.mol.single_bar, self._spin).transpose(), self._spin).real
+            self.mol.double_bar = block.transpose(0, 2, 1, 3) - block.transpose(0, 2, 3, 1)
+
+    def MP2(self, spin_orbital=False):
+        mol = self.mol
+        if spin_orbital:
+            self._ensure_double_bar()
+            acc = 0.0
+            occ, virt = range(mol.nelec), range(mol.nelec, mol.norb)
+            for i, j, a, b in product(occ, occ, virt, virt):
+                acc += mol.double_bar[i, j, a, b] ** 2 / (mol.fs[i, i] + mol.fs[j, j] - mol.fs[a, a] - mol.fs[b, b])
+            mol.emp2 = 0.25 * acc + mol.energy
+        else:
+            acc = 0.0
+            occ, virt = range(mol.nocc), range(mol.nocc, mol.nbasis)
+            g = mol.single_bar
+            for i, j, a, b in product(occ, occ, virt, virt):
+                denom = mol.MO[i] + mol.MO[j] - mol.MO[a] - mol.MO[b]
+                acc += g[i, a, j, b] * (2.0 * g[i, a, j, b] - g[i, b, j, a]) / denom
+            mol.emp2 = acc + mol.energy
+        print("E(MP2) = ", mol.emp2.real)
