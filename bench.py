@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line per run (contract in the task statement).
+
+A "step" is ONE complete integral-direct Fock build G(dP) of the workload molecule: shell-level
+Schwarz x density screening, every ERI class kernel with fused J/K digestion, and (N > 1) the
+all-reduce of the partial G matrices.  dP = the core-Hamiltonian-guess density (first SCF iteration,
+nothing screened by the density), tol = 1e-12 — SURVEY.md §8(d).
+
+    value   screened contracted shell quartets evaluated per second, whole job (all ranks), inputs
+            (dP, Schwarz data, pair tables) resident in HBM, CUDA-event timed, max over ranks
+    e2e     the same metric through the reference-facing call formPT(P, P_old, bfs, N, screen, tol)
+            with host numpy buffers (H2D of dP and D2H of G inside the timed region)
+    roofline  the dominant ERI class kernel: algorithmic FP64 FLOPs (SURVEY §8d model) / its event time,
+            against the FP64 FMA issue peak measured live by the DFMA probe (MEASURED_PEAKS.json has
+            no FP64 entry)
+    cpu_baseline  the reference's own Cython ERI (oracle/_ref) timed on this box's host cores on a
+            bounded stratified sample of the same surviving quartets
+
+`--impl reference` times the reference's CPU implementation alone (no GPU code on that path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "mcmurchie-davidson_b200")
+SAMPLES = os.path.join(ROOT, "bench_samples")
+METRIC = "screened_eri_shell_quartets_per_s_direct_fock_build"
+UNIT = "quartets/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MMDB_BENCH_WORKLOAD", "w32_ccpvdz"))
+    ap.add_argument("--cpu-baseline", type=int, default=1, help="0 skips the cpu_baseline leg")
+    ap.add_argument("--class-timing", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks(object):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.2] or self.rows
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU timing on a bounded sample (subprocess: imports the reference's own `mmd`)
+# ------------------------------------------------------------------------------------------------
+REF_WORKER = r'''
+import json, sys, time, os
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from mmd.molecule import Molecule
+from mmd.integrals.twoe import ERI
+import multiprocessing as mp
+spec = json.load(open(sys.argv[2]))
+nproc = int(sys.argv[3]); steps = int(sys.argv[4]); warm = int(sys.argv[5])
+mol = Molecule(geometry=spec["geometry"], basis=spec["basis"])
+bfs = mol.bfs
+quartets = spec["quartets"]            # list of [class_key, [[i,j,k,l], ...]] : the function quartets of one shell quartet
+def work(chunk):
+    t0 = time.perf_counter(); n = 0
+    for key, fns in chunk:
+        for i, j, k, l in fns:
+            ERI(bfs[i], bfs[j], bfs[k], bfs[l]); n += 1
+    return time.perf_counter() - t0, n
+def one_pass():
+    chunks = [quartets[r::nproc] for r in range(nproc)]
+    t0 = time.perf_counter()
+    if nproc == 1:
+        res = [work(chunks[0])]
+    else:
+        with mp.get_context("fork").Pool(nproc) as pool:
+            res = pool.map(work, chunks)
+    return time.perf_counter() - t0, sum(r[0] for r in res), sum(r[1] for r in res)
+# per-class single-core cost (for extrapolation to the class populations)
+for _ in range(warm): one_pass()
+walls = [];
+for _ in range(steps):
+    w, cpu, nint = one_pass(); walls.append(w)
+per_class = {}
+t_class = {}
+for key, fns in quartets:
+    t0 = time.perf_counter()
+    for i, j, k, l in fns: ERI(bfs[i], bfs[j], bfs[k], bfs[l])
+    dt = time.perf_counter() - t0
+    t_class.setdefault(key, []).append(dt)
+print(json.dumps({"walls": walls, "n_shell_quartets": len(quartets), "n_integrals": nint,
+                  "class_mean_s": {k: float(np.mean(v)) for k, v in t_class.items()}}))
+'''
+
+
+def reference_timing(sample_path, nproc, steps, warm):
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "mmd")):
+        return None, "oracle/_ref not built"
+    out = subprocess.run([sys.executable, "-c", REF_WORKER, ref, sample_path, str(nproc), str(steps), str(warm)],
+                         capture_output=True, text=True, timeout=3000)
+    if out.returncode != 0:
+        return None, out.stderr[-400:]
+    return json.loads(out.stdout.strip().splitlines()[-1]), None
+
+
+def load_sample(workload):
+    path = os.path.join(SAMPLES, workload + ".json")
+    return path if os.path.exists(path) else None
+
+
+def reference_value(res, spec):
+    """Sample -> whole-workload shell quartets/s: populations of every class x mean sampled time."""
+    pops = spec["class_quartets"]
+    t_total = sum(pops[k] * res["class_mean_s"][k] for k in pops if k in res["class_mean_s"])
+    n_total = sum(pops[k] for k in pops if k in res["class_mean_s"])
+    return n_total / t_total      # single-core quartets/s
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = load_sample(a.workload)
+    if sample is None:
+        print(json.dumps({"impl": "reference", "unavailable": "bench_samples/%s.json missing" % a.workload}))
+        return
+    spec = json.load(open(sample))
+    cores = os.cpu_count() or 1
+    res, err = reference_timing(sample, cores, a.steps, a.warmup)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": err}))
+        return
+    wall = sum(res["walls"]) / len(res["walls"])
+    single = reference_value(res, spec)
+    # all host cores, measured: sample quartets / wall per pass, rescaled from the sample's class mix to
+    # the workload's class mix through the single-core per-class costs
+    t_sample_1core = sum(res["class_mean_s"][k] for k, _ in spec["quartets"])
+    speedup = t_sample_1core / wall
+    value = single * speedup
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": spec["workload_desc"], "sample": "%d surviving shell quartets (%d contracted integrals) per step, stratified over %d classes" % (
+                res["n_shell_quartets"], res["n_integrals"], len(res["class_mean_s"]))},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": "reference Cython ERI (oracle/_ref) on the stratified quartet sample, %d processes; single-core rate %.1f quartets/s extrapolated by class populations" % (cores, single)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main_ours(a):
+    sys.path.insert(0, PKG)
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mmd._b200 import engine as E, lib as L, synth
+    from mmd.molecule import Molecule
+    import scipy.linalg
+
+    geom, basis = synth.config(a.workload)
+    mol = Molecule(geom, basis)
+    N = mol.nbasis
+    eng = mol.engine
+    mol.one_electron_integrals()
+    FO = mol.X.T @ mol.Core @ mol.X
+    _, CO = scipy.linalg.eigh(FO)
+    Cm = mol.X @ CO
+    P = (Cm[:, :mol.nocc] @ Cm[:, :mol.nocc].conj().T).astype(complex)
+    scr = eng.schwarz()
+    tol = 1e-12
+    dev = eng.tdev
+    dP = torch.from_numpy(np.ascontiguousarray(P.real)).to(dev)
+    G = torch.zeros((N, N), dtype=torch.float64, device=dev)
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(stats=None, flags=0):
+        G.zero_()
+        L.check(eng.lib.mmdb_fock_direct(eng.h, L.ptr(dP), None, tol, L.ptr(G), None, rank, world, flags,
+                                         C.byref(stats) if stats is not None else None, C.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.all_reduce(G)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    # un-timed pass with per-class events: stats for the roofline line and the class table
+    stats = L.FockStats()
+    step(stats, flags=1 if a.class_timing else 0)
+    torch.cuda.synchronize()
+    st = stats.as_dict()
+
+    clocks = Clocks(local)
+    clocks.start()
+    barrier()
+    t_w0 = time.time()
+    evs = []
+    for _ in range(a.steps):
+        flush.fill_(1.0)                          # L2 flush between timed steps (outside the event pairs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_w1 = time.time()
+    ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    clk = clocks.stop(t_w0, t_w1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    q = torch.tensor([float(st["quartets"]), float(st["prim_quartets"]), float(st["fn_quartets"]), float(st["model_flops"])],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(q)
+    ms_step = float(t.item()) / a.steps
+    quartets, primq, fnq, mflops = (float(x) for x in q.tolist())
+    value = quartets / (ms_step * 1e-3)
+
+    # ---- e2e through the reference-facing call with host buffers ---------------------------------
+    from mmd.integrals.fock import formPT
+    Z = np.zeros_like(P)
+    for _ in range(2):
+        formPT(P, Z, mol.bfs, N, scr, tol)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        Gh = formPT(P, Z, mol.bfs, N, scr, tol)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / a.steps
+    tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_value = quartets / float(tt.item())
+    parity = float(np.abs(Gh.real - G.cpu().numpy()).max())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    peak_tf, _ = E.fp64_peak(local)
+    roof = None
+    if a.class_timing and st["classes"]:
+        name, c = max(st["classes"].items(), key=lambda kv: kv[1]["ms"])
+        fl = c["prim_quartets"] * c["flops_per_prim_quartet"]
+        ach = fl / (c["ms"] * 1e-3) / 1e12
+        roof = {"bound": "fp64_fma", "kernel": "eri_class_kernel %s fused J/K digestion" % name, "achieved": ach, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": "measured live: DFMA issue probe mmdb_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; nominal 37.2)",
+                "launch_ms": c["ms"], "share_of_step": c["ms"] / sum(x["ms"] + x["screen_ms"] for x in st["classes"].values()),
+                "whole_build": {"model_gflop": mflops / 1e9, "achieved_tflops": mflops / (ms_step * 1e-3) / 1e12,
+                                "frac": mflops / (ms_step * 1e-3) / 1e12 / (peak_tf * world)}}
+    launches = 2 + 2 * len(st["classes"]) + 1      # dabs + dshell + (screen + ERI) per class + zero
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "%s direct RHF Fock build, N=%d Cartesian functions, first-iteration density, tol 1e-12" % (a.workload, N),
+                       "l2": "per-step working set (compact quartet lists, >2 GB) exceeds L2; plus an explicit 512 MiB flush between timed steps",
+                       "parallelism": "quartet-sharded x%d + allreduce(G)" % world if world > 1 else "1 GPU"},
+            "fock_builds_per_s": 1e3 / ms_step, "prim_quartets_per_s": primq / (ms_step * 1e-3),
+            "contracted_integrals_per_s": fnq / (ms_step * 1e-3), "quartets_per_build": quartets,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N * N, "d2h_bytes_per_step": 8 * N * N,
+                    "ms_per_step": 1e3 * float(tt.item()), "max_abs_diff_vs_device_path": parity},
+            "gpu_launches": launches * a.steps, "clocks": clk, "roofline": roof,
+            "classes": {k: {"quartets": v["quartets"], "prim_quartets": v["prim_quartets"], "ms": round(v["ms"], 4),
+                            "screen_ms": round(v["screen_ms"], 4),
+                            "tflops": v["prim_quartets"] * v["flops_per_prim_quartet"] / max(v["ms"], 1e-9) / 1e9}
+                        for k, v in st["classes"].items()} if a.class_timing else None}
+    # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    if world == 1 and a.cpu_baseline:
+        sample = load_sample(a.workload)
+        if sample is not None:
+            spec = json.load(open(sample))
+            res, err = reference_timing(sample, 1, 1, 0)
+            if res is not None:
+                v1 = reference_value(res, spec)
+                line["cpu_baseline"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "reference",
+                                        "sample": "reference Cython ERI (oracle/_ref), 1 core, %d surviving shell quartets (%d integrals) stratified over %d classes, extrapolated by class populations; formPT's ~6.4 us/candidate Python loop overhead NOT included" % (
+                                            res["n_shell_quartets"], res["n_integrals"], len(res["class_mean_s"])),
+                                        "host_cores_available": os.cpu_count()}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "failed: %s" % err}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "bench_samples/%s.json missing" % a.workload}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)

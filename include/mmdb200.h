@@ -102,7 +102,8 @@ typedef struct {
     double model_flops;       /* sum over classes of prim_quartets(class) * F(class), SURVEY §8d */
     int64_t class_quartets[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];
     int64_t class_prim_quartets[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];
-    float class_ms[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR]; /* per-class kernel time when timing enabled */
+    float class_ms[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];        /* ERI+digestion kernel time per class (flags bit0) */
+    float class_screen_ms[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR]; /* screening kernel time per class (flags bit0)     */
 } mmdb_fock_stats;
 
 /* Direct Fock build (cython/fock.pyx:13-87): G += contributions of every canonical basis-function

@@ -628,7 +628,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     dshell_kernel<<<(b->nshell * b->nshell + 127) / 128, 128, 0, st>>>(b->Dabs_dev, N, b->sh_bf0_dev, b->sh_nf_dev,
                                                                        b->nshell, b->DS_dev, b->dglob_dev);
     CU(cudaMemsetAsync(b->ctr_dev, 0, sizeof(unsigned long long) * b->nctr, st));
-    struct Launch { int cb, ck, slot; cudaEvent_t e0, e1; };
+    struct Launch { int cb, ck, slot; cudaEvent_t e0, em, e1; };
     std::vector<Launch> launches;
     const bool timing = (flags & 1) != 0;
     int slot = 0;
@@ -641,13 +641,15 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                 const int row1 = (int)std::min<size_t>(B.npairs, row0 + rows_per);
                 CHK(ensure_list(b, (size_t)(row1 - row0) * K.npairs));
                 if (slot * 3 + 2 >= b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
-                Launch ln{cb, ck, slot, nullptr, nullptr};
+                Launch ln{cb, ck, slot, nullptr, nullptr, nullptr};
                 if (timing) {
                     CU(cudaEventCreate(&ln.e0));
+                    CU(cudaEventCreate(&ln.em));
                     CU(cudaEventCreate(&ln.e1));
                     CU(cudaEventRecord(ln.e0, st));
                 }
                 CHK(run_screen(b, B, K, cb == ck, row0, row1, shard, nshards, false, tol, slot, st));
+                if (timing) CU(cudaEventRecord(ln.em, st));
                 EriArgs a;
                 std::memset(&a, 0, sizeof(a));
                 a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
@@ -678,15 +680,17 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             stats->class_prim_quartets[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += npq;
             if (timing) {
                 float ms = 0.f;
-                cudaEventElapsedTime(&ms, ln.e0, ln.e1);
+                cudaEventElapsedTime(&ms, ln.em, ln.e1);
                 stats->class_ms[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += ms;
+                cudaEventElapsedTime(&ms, ln.e0, ln.em);
+                stats->class_screen_ms[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += ms;
             }
         }
     } else if (timing) {
         CU(cudaStreamSynchronize(st));
     }
     for (auto &ln : launches)
-        if (ln.e0) { cudaEventDestroy(ln.e0); cudaEventDestroy(ln.e1); }
+        if (ln.e0) { cudaEventDestroy(ln.e0); cudaEventDestroy(ln.em); cudaEventDestroy(ln.e1); }
     CU(cudaGetLastError());
     return MMDB_OK;
 }

@@ -9,6 +9,7 @@ import os
 
 import numpy as np
 
+from . import dist as D
 from . import lib as L
 from .shells import ShellTable
 
@@ -231,10 +232,7 @@ class Engine(object):
         dPd = self.table.to_dev_matrix(dP)
         n = self.Ndev
         cplx = np.iscomplexobj(dPd) and bool(np.any(dPd.imag != 0.0))
-        rank, world = 0, 1
-        dist = torch.distributed
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            rank, world = dist.get_rank(), dist.get_world_size()
+        rank, world = D.world()
         with torch.cuda.device(self.tdev):
             re = torch.from_numpy(np.ascontiguousarray(dPd.real, dtype=np.float64)).to(self.tdev)
             im = torch.from_numpy(np.ascontiguousarray(dPd.imag, dtype=np.float64)).to(self.tdev) if cplx else None
@@ -243,8 +241,7 @@ class Engine(object):
             L.check(self.lib.mmdb_fock_direct(self.h, L.ptr(re), L.ptr(im), float(tol), L.ptr(G[0]),
                                               L.ptr(G[1]) if cplx else None, rank, world, int(flags),
                                               C.byref(stats) if want_stats else None, self._stream()))
-            if world > 1:
-                dist.all_reduce(G)
+            D.allreduce_sum_(G)
             g = G.cpu().numpy()
         self.last_stats = stats.as_dict() if want_stats else None
         out = g[0].astype(np.complex128)

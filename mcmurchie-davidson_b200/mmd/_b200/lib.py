@@ -29,6 +29,7 @@ class FockStats(C.Structure):
         ("class_quartets", C.c_int64 * (NCLASS_PAIR * NCLASS_PAIR)),
         ("class_prim_quartets", C.c_int64 * (NCLASS_PAIR * NCLASS_PAIR)),
         ("class_ms", C.c_float * (NCLASS_PAIR * NCLASS_PAIR)),
+        ("class_screen_ms", C.c_float * (NCLASS_PAIR * NCLASS_PAIR)),
     ]
 
     def as_dict(self):
@@ -43,6 +44,8 @@ class FockStats(C.Structure):
                         "quartets": q,
                         "prim_quartets": self.class_prim_quartets[cb * NCLASS_PAIR + ck],
                         "ms": self.class_ms[cb * NCLASS_PAIR + ck],
+                        "screen_ms": self.class_screen_ms[cb * NCLASS_PAIR + ck],
+                        "flops_per_prim_quartet": class_flops(*(PAIR_CLASSES[cb] + PAIR_CLASSES[ck])),
                     }
         d["classes"] = per
         return d

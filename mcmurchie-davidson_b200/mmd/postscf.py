@@ -18,12 +18,18 @@ class PostSCF(object):
         self.ao2mo()
 
     def ao2mo(self):
-        """(pq|rs) -> MO basis by four quarter transformations; mol.single_bar[P,Q,R,S]."""
+        """(pq|rs) -> MO basis by four quarter transformations; mol.single_bar[P,Q,R,S].
+
+        Bra orbitals (first and third index of the chemists' (PQ|RS)) are complex-conjugated.  For real
+        orbitals this is the reference's transformation (mmd/postscf.py:26-27); when LAPACK returns a
+        complex rotation inside a degenerate orbital set (X = S^-1/2 carries ~1e-17 imaginary noise,
+        e.g. CH4) it keeps E(MP2) invariant, where the un-conjugated form would not be."""
         C = self.mol.C
+        Cc = np.conjugate(C)
         t = np.einsum("pqrs,sS->pqrS", self.mol.TwoE, C, optimize=True)
-        t = np.einsum("pqrS,rR->pqRS", t, C, optimize=True)
+        t = np.einsum("pqrS,rR->pqRS", t, Cc, optimize=True)
         t = np.einsum("pqRS,qQ->pQRS", t, C, optimize=True)
-        self.mol.single_bar = np.einsum("pQRS,pP->PQRS", t, C, optimize=True)
+        self.mol.single_bar = np.einsum("pQRS,pP->PQRS", t, Cc, optimize=True)
         self.mol.norb = self.mol.nbasis * 2
         self._spin = np.eye(2)
         # spin-orbital quantities are O((2N)^4) and only needed for spin_orbital=True: built lazily
@@ -50,6 +56,6 @@ class PostSCF(object):
             g = mol.single_bar
             for i, j, a, b in product(occ, occ, virt, virt):
                 denom = mol.MO[i] + mol.MO[j] - mol.MO[a] - mol.MO[b]
-                acc += g[i, a, j, b] * (2.0 * g[i, a, j, b] - g[i, b, j, a]) / denom
+                acc += np.conjugate(g[i, a, j, b]) * (2.0 * g[i, a, j, b] - g[i, b, j, a]) / denom
             mol.emp2 = acc + mol.energy
         print("E(MP2) = ", mol.emp2.real)

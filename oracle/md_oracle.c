@@ -391,3 +391,144 @@ void mdo_jk_incore(long N, const double *TwoE, const double *P, double *J, doubl
             K[2 * (p * N + q)] = kr; K[2 * (p * N + q) + 1] = ki;
         }
 }
+
+/* =============================================================================================
+ * One-electron integrals (cython/onee.pyx) — checker for the enabler kernel csrc/onee.cu
+ * ============================================================================================= */
+static double E_neg(int i, int j, int t, double Q, double a, double b)
+{
+    /* E with possibly negative j as the reference's kinetic() may call it: every such term is
+       multiplied by a zero coefficient there; return 0 like the reference's recursion bottom. */
+    if (i < 0 || j < 0) return 0.0;
+    return mdo_E(i, j, t, Q, a, b);
+}
+
+/* onee.pyx:71-78 */
+static double p_overlap(double a, const long *l1, const double *A, double b, const long *l2, const double *B)
+{
+    return mdo_E(l1[0], l2[0], 0, A[0] - B[0], a, b) * mdo_E(l1[1], l2[1], 0, A[1] - B[1], a, b) *
+           mdo_E(l1[2], l2[2], 0, A[2] - B[2], a, b) * pow(MDO_PI / (a + b), 1.5);
+}
+
+/* onee.pyx:108-137 */
+static double p_kinetic(double a, const long *l1, const double *A, double b, const long *l2, const double *B)
+{
+    double T[3], S[3];
+    for (int d = 0; d < 3; ++d) S[d] = mdo_E(l1[d], l2[d], 0, A[d] - B[d], a, b);
+    for (int d = 0; d < 3; ++d) {
+        double Ad = (2 * l2[d] + 1) * b, Bd = -2 * pow(b, 2), Cd = -0.5 * l2[d] * (l2[d] - 1);
+        T[d] = Ad * mdo_E(l1[d], l2[d], 0, A[d] - B[d], a, b) + Bd * mdo_E(l1[d], l2[d] + 2, 0, A[d] - B[d], a, b) +
+               Cd * E_neg(l1[d], l2[d] - 2, 0, A[d] - B[d], a, b);
+    }
+    double Tx = T[0] * S[1] * S[2], Ty = T[1] * S[0] * S[2], Tz = T[2] * S[0] * S[1];
+    return (Tx + Ty + Tz) * pow(MDO_PI / (a + b), 1.5);
+}
+
+/* onee.pyx:81-106 */
+static double p_dipole(double a, const long *l1, const double *A, double b, const long *l2, const double *B,
+                       const double *C, int dir)
+{
+    double p = a + b, S[3], D;
+    for (int d = 0; d < 3; ++d) S[d] = mdo_E(l1[d], l2[d], 0, A[d] - B[d], a, b);
+    double Pd = (a * A[dir] + b * B[dir]) / p;
+    D = mdo_E(l1[dir], l2[dir], 1, A[dir] - B[dir], a, b) + (Pd - C[dir]) * S[dir];
+    S[dir] = D;
+    return S[0] * S[1] * S[2] * pow(MDO_PI / p, 1.5);
+}
+
+/* onee.pyx:140-176 */
+static double p_angular(double a, const long *l1, const double *A, double b, const long *l2, const double *B,
+                        const double *C, int dir)
+{
+    double S0[3], S1[3], D1[3];
+    for (int d = 0; d < 3; ++d) {
+        double Q = A[d] - B[d];
+        S0[d] = mdo_E(l1[d], l2[d], 0, Q, a, b);
+        S1[d] = mdo_E(l1[d] + 1, l2[d], 0, Q, a, b) + (A[d] - C[d]) * mdo_E(l1[d], l2[d], 0, Q, a, b); /* util.pxi:27-28 */
+        D1[d] = l2[d] * E_neg(l1[d], l2[d] - 1, 0, Q, a, b) - 2 * b * mdo_E(l1[d], l2[d] + 1, 0, Q, a, b);
+    }
+    double pf = pow(MDO_PI / (a + b), 1.5);
+    if (dir == 0) return -S0[0] * (S1[1] * D1[2] - S1[2] * D1[1]) * pf;
+    if (dir == 1) return -S0[1] * (S1[2] * D1[0] - S1[0] * D1[2]) * pf;
+    return -S0[2] * (S1[0] * D1[1] - S1[1] * D1[0]) * pf;
+}
+
+/* onee.pyx:178-192 */
+static double p_nuclear(double a, const long *l1, const double *A, double b, const long *l2, const double *B,
+                        const double *C)
+{
+    double p = a + b;
+    double P[3];
+    for (int d = 0; d < 3; ++d) P[d] = (a * A[d] + b * B[d]) / p;
+    double RPC = sqrt((P[0] - C[0]) * (P[0] - C[0]) + (P[1] - C[1]) * (P[1] - C[1]) + (P[2] - C[2]) * (P[2] - C[2]));
+    double leaf[MDO_MAXN];
+    int L = (int)(l1[0] + l1[1] + l1[2] + l2[0] + l2[1] + l2[2]);
+    R_leaves(L, p, RPC, leaf);
+    double val = 0.0;
+    for (int t = 0; t <= l1[0] + l2[0]; ++t)
+        for (int u = 0; u <= l1[1] + l2[1]; ++u)
+            for (int v = 0; v <= l1[2] + l2[2]; ++v)
+                val += mdo_E(l1[0], l2[0], t, A[0] - B[0], a, b) * mdo_E(l1[1], l2[1], u, A[1] - B[1], a, b) *
+                       mdo_E(l1[2], l2[2], v, A[2] - B[2], a, b) *
+                       R_rec(t, u, v, 0, leaf, P[0] - C[0], P[1] - C[1], P[2] - C[2]);
+    return val * 2 * MDO_PI / p;
+}
+
+typedef struct {
+    const mdo_basis *bs; long N; long natom; const double *Z, *xyz, *origin;
+    double *S, *T, *V, *M, *L;
+} onee_ctx;
+
+/* mmd/molecule.py:253-276: rows i, columns j <= i, mirrored (L antisymmetric, diagonal ends -L_ii) */
+static void onee_row(long i, void *v)
+{
+    onee_ctx *c = (onee_ctx *)v;
+    const mdo_basis *bs = c->bs;
+    long N = c->N;
+    for (long j = 0; j <= i; ++j) {
+        double s = 0, t = 0, mu[3] = {0, 0, 0}, ll[3] = {0, 0, 0};
+        const long *la = bs->shell + 3 * i, *lb = bs->shell + 3 * j;
+        const double *A = bs->origin + 3 * i, *B = bs->origin + 3 * j;
+        for (long ia = 0; ia < bs->nprim[i]; ++ia)
+            for (long ib = 0; ib < bs->nprim[j]; ++ib) {
+                double ea = bs->exps[bs->off[i] + ia], eb = bs->exps[bs->off[j] + ib];
+                double w = bs->norm[bs->off[i] + ia] * bs->norm[bs->off[j] + ib] * bs->coefs[bs->off[i] + ia] *
+                           bs->coefs[bs->off[j] + ib];
+                s += w * p_overlap(ea, la, A, eb, lb, B);
+                t += w * p_kinetic(ea, la, A, eb, lb, B);
+                for (int d = 0; d < 3; ++d) {
+                    mu[d] += w * p_dipole(ea, la, A, eb, lb, B, c->origin, d);
+                    ll[d] += w * p_angular(ea, la, A, eb, lb, B, c->origin, d);
+                }
+            }
+        double vv = 0.0;
+        for (long at = 0; at < c->natom; ++at) {
+            double va = 0.0;
+            for (long ia = 0; ia < bs->nprim[i]; ++ia)
+                for (long ib = 0; ib < bs->nprim[j]; ++ib) {
+                    double ea = bs->exps[bs->off[i] + ia], eb = bs->exps[bs->off[j] + ib];
+                    double w = bs->norm[bs->off[i] + ia] * bs->norm[bs->off[j] + ib] * bs->coefs[bs->off[i] + ia] *
+                               bs->coefs[bs->off[j] + ib];
+                    va += w * p_nuclear(ea, la, A, eb, lb, B, c->xyz + 3 * at);
+                }
+            vv += -c->Z[at] * va;
+        }
+        c->S[i * N + j] = c->S[j * N + i] = s;
+        c->T[i * N + j] = c->T[j * N + i] = t;
+        c->V[i * N + j] = c->V[j * N + i] = vv;
+        for (int d = 0; d < 3; ++d) {
+            c->M[d * N * N + i * N + j] = c->M[d * N * N + j * N + i] = mu[d];
+            c->L[d * N * N + i * N + j] = ll[d];
+            c->L[d * N * N + j * N + i] = -ll[d];
+        }
+    }
+}
+
+void mdo_onee(long N, long natom, const double *Z, const double *xyz, const double *origin3, double *S, double *T,
+              double *V, double *M, double *L, const double *origin, const long *shell, const long *nprim,
+              const long *off, const double *exps, const double *coefs, const double *norm)
+{
+    mdo_basis bs = mk(N, origin, shell, nprim, off, exps, coefs, norm);
+    onee_ctx c = {&bs, N, natom, Z, xyz, origin3, S, T, V, M, L};
+    parallel_for(N, onee_row, &c);
+}

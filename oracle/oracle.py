@@ -50,6 +50,8 @@ def lib():
         L.mdo_schwarz.argtypes = [C.c_long, _dp] + basis
         L.mdo_formPT.restype = None
         L.mdo_formPT.argtypes = [C.c_long, _dp, _dp, _dp, C.c_double, _dp, C.POINTER(C.c_long)] + basis
+        L.mdo_onee.restype = None
+        L.mdo_onee.argtypes = [C.c_long, C.c_long, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp] + basis
         L.mdo_jk_incore.restype = None
         L.mdo_jk_incore.argtypes = [C.c_long, _dp, _dp, _dp, _dp]
         _LIB = L
@@ -155,3 +157,16 @@ def jk_incore(TwoE, P):
     lib().mdo_jk_incore(N, T.reshape(-1), Pc.view(np.float64).reshape(-1), J.view(np.float64).reshape(-1),
                         K.view(np.float64).reshape(-1))
     return J, K
+
+
+def onee(bfs, charges, coords, origin):
+    """S, T, V (N,N), M (3,N,N), L (3,N,N) as mmd/molecule.py:235-276 assembles them from cython/onee.pyx."""
+    fb = _fb(bfs)
+    N = fb.nbf
+    Z = np.ascontiguousarray(charges, dtype=np.float64)
+    xyz = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1)
+    org = np.ascontiguousarray(origin, dtype=np.float64)
+    S = np.zeros((N, N)); T = np.zeros((N, N)); V = np.zeros((N, N))
+    M = np.zeros((3, N, N)); Lm = np.zeros((3, N, N))
+    lib().mdo_onee(N, len(Z), Z, xyz, org, S.reshape(-1), T.reshape(-1), V.reshape(-1), M.reshape(-1), Lm.reshape(-1), *fb.args())
+    return S, T, V, M, Lm
