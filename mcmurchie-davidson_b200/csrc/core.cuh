@@ -84,6 +84,36 @@ struct __align__(16) PairHdr {    // one shell pair, 64 B
     double Qs;                     // max over function pairs sqrt|(pq|pq)|  (filled by mmdb_schwarz)
 };
 
+
+// ------------------------------------------------------------------------------------------
+// explicit global-space accessors: the kernels receive their pointers inside a by-value struct, so
+// the compiler cannot prove the address space and would emit generic LD / ATOM with run-time
+// space checks (QSPC + shared-memory CAS fallback).  These force LDG(.nc) and RED.global.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_f64(double *p, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ PrimPair ld_prim(const PrimPair *p)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    PrimPair r;
+    r.Px = a.x; r.Py = a.y; r.Pz = b.x; r.p = b.y; r.cc = c.x; r.PAx = c.y; r.PAy = d.x; r.PAz = d.y;
+    return r;
+}
+__device__ __forceinline__ PairHdr ld_hdr(const PairHdr *p)
+{
+    const int4 *qi = reinterpret_cast<const int4 *>(p);
+    const int4 a = __ldg(qi), b = __ldg(qi + 1);
+    const double2 *qd = reinterpret_cast<const double2 *>(p) + 2;
+    const double2 c = __ldg(qd), d = __ldg(qd + 1);
+    PairHdr r;
+    r.bfA = a.x; r.bfB = a.y; r.poff = a.z; r.pnum = a.w; r.shA = b.x; r.shB = b.y; r.pad0 = b.z; r.pad1 = b.w;
+    r.ABx = c.x; r.ABy = c.y; r.ABz = d.x; r.Qs = d.y;
+    return r;
+}
+
 // Boys table: rows T0 = i/8, i = 0..320; columns k = 0..8: F_{L+k}(T0)/k!, column 9: exp(-T0).
 constexpr int BOYS_ROWS = 321;
 constexpr int BOYS_STRIDE = 10;
@@ -272,7 +302,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
     for (int x = 0; x < NAB * NCDC; ++x) out[x] = 0.0;
 
     for (int ib = 0; ib < bh.pnum; ++ib) {
-        const PrimPair b = bp[bh.poff + ib];
+        const PrimPair b = ld_prim(bp + bh.poff + ib);
         ETab<LA, LB> Eb;
         {
             const double PA[3] = {b.PAx, b.PAy, b.PAz};
@@ -284,7 +314,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
         for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
 
         for (int ik = 0; ik < kh.pnum; ++ik) {
-            const PrimPair k = kp[kh.poff + ik];
+            const PrimPair k = ld_prim(kp + kh.poff + ik);
             const double pq = b.p + k.p;
             const double ipq = 1.0 / pq;
             const double alpha = b.p * k.p * ipq;
@@ -393,9 +423,9 @@ __device__ __forceinline__ void digest_fn_quartet(const DigestArgs &g, int i, in
     }
     const int N = g.N;
     const double *D = g.Dabs;
-    double bound = g.SQ[i * N + j] * g.SQ[k * N + l];                       // fock.pyx:46-47
-    double dmax = fmax(4.0 * D[i * N + j], 4.0 * D[k * N + l]);             // fock.pyx:49-54
-    dmax = fmax(dmax, fmax(fmax(D[i * N + k], D[i * N + l]), fmax(D[j * N + k], D[j * N + l])));
+    double bound = __ldg(&g.SQ[i * N + j]) * __ldg(&g.SQ[k * N + l]);                       // fock.pyx:46-47
+    double dmax = fmax(4.0 * __ldg(&D[i * N + j]), 4.0 * __ldg(&D[k * N + l]));             // fock.pyx:49-54
+    dmax = fmax(dmax, fmax(fmax(__ldg(&D[i * N + k]), __ldg(&D[i * N + l])), fmax(__ldg(&D[j * N + k]), __ldg(&D[j * N + l]))));
     bound *= dmax;
     if (bound < g.tol) return;                                              // fock.pyx:56-57
     double deg = (i == j) ? 1.0 : 2.0;                                      // fock.pyx:60-70
@@ -404,20 +434,20 @@ __device__ __forceinline__ void digest_fn_quartet(const DigestArgs &g, int i, in
     const double e = deg * val;                                            // fock.pyx:74-75
     const double eq = -0.25 * e;
     const double *P = g.dPre;
-    atomicAdd(&g.Gre[i * N + j], P[k * N + l] * e);                         // fock.pyx:79
-    atomicAdd(&g.Gre[k * N + l], P[i * N + j] * e);                         // fock.pyx:80
-    atomicAdd(&g.Gre[i * N + k], P[j * N + l] * eq);                        // fock.pyx:82
-    atomicAdd(&g.Gre[j * N + l], P[i * N + k] * eq);                        // fock.pyx:83
-    atomicAdd(&g.Gre[i * N + l], P[j * N + k] * eq);                        // fock.pyx:84
-    atomicAdd(&g.Gre[k * N + j], P[i * N + l] * eq);                        // fock.pyx:85
+    red_add_f64(&g.Gre[i * N + j], __ldg(&P[k * N + l]) * e);                         // fock.pyx:79
+    red_add_f64(&g.Gre[k * N + l], __ldg(&P[i * N + j]) * e);                         // fock.pyx:80
+    red_add_f64(&g.Gre[i * N + k], __ldg(&P[j * N + l]) * eq);                        // fock.pyx:82
+    red_add_f64(&g.Gre[j * N + l], __ldg(&P[i * N + k]) * eq);                        // fock.pyx:83
+    red_add_f64(&g.Gre[i * N + l], __ldg(&P[j * N + k]) * eq);                        // fock.pyx:84
+    red_add_f64(&g.Gre[k * N + j], __ldg(&P[i * N + l]) * eq);                        // fock.pyx:85
     if (g.dPim != nullptr) {
         const double *Q = g.dPim;
-        atomicAdd(&g.Gim[i * N + j], Q[k * N + l] * e);
-        atomicAdd(&g.Gim[k * N + l], Q[i * N + j] * e);
-        atomicAdd(&g.Gim[i * N + k], Q[j * N + l] * eq);
-        atomicAdd(&g.Gim[j * N + l], Q[i * N + k] * eq);
-        atomicAdd(&g.Gim[i * N + l], Q[j * N + k] * eq);
-        atomicAdd(&g.Gim[k * N + j], Q[i * N + l] * eq);
+        red_add_f64(&g.Gim[i * N + j], __ldg(&Q[k * N + l]) * e);
+        red_add_f64(&g.Gim[k * N + l], __ldg(&Q[i * N + j]) * e);
+        red_add_f64(&g.Gim[i * N + k], __ldg(&Q[j * N + l]) * eq);
+        red_add_f64(&g.Gim[j * N + l], __ldg(&Q[i * N + k]) * eq);
+        red_add_f64(&g.Gim[i * N + l], __ldg(&Q[j * N + k]) * eq);
+        red_add_f64(&g.Gim[k * N + j], __ldg(&Q[i * N + l]) * eq);
     }
 }
 

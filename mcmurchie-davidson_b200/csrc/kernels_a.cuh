@@ -20,64 +20,267 @@ __host__ __device__ constexpr int chunk_ncd()
     return best;
 }
 
+// ------------------------------------------------------------------------------------------
+// Shell-level digestion (fast path).  Preconditions, checked by the caller: real density, shells
+// A != B, C != D and the higher-indexed shells of bra and ket differ — then the canonical order
+// i>=j, k>=l, ij>=kl of cython/fock.pyx:38-44 is the same for every function quartet of the block
+// and the degeneracy is 8.  All density / Schwarz elements the block needs are loaded up front
+// (independent loads, one latency exposure), the six updates of fock.pyx:79-85 are accumulated in
+// registers per destination element, and each destination element receives ONE atomic.
+// Orientation: J blocks are stored [hi,lo]; exchange blocks [canonical-bra fn, canonical-ket fn]
+// except (lo of canonical bra, hi of canonical ket) which the reference stores transposed (G[k,j]).
+// ------------------------------------------------------------------------------------------
+struct BlockAddr {
+    long long base;   // element offset of (0,0)
+    int s0, s1;       // strides of the first / second block index
+};
+
+struct DigestGeom {
+    BlockAddr ab, cd;                 // J blocks, P and G share the address
+    BlockAddr pac, pad, pbc, pbd;     // P reads of the exchange blocks
+    BlockAddr gac, gad, gbc, gbd;     // G writes of the exchange blocks
+};
+
+__device__ __forceinline__ DigestGeom make_geom(int N, int bfA, int bfB, int bfC, int bfD)
+{
+    DigestGeom g;
+    const bool aHi = bfA > bfB, cHi = bfC > bfD;
+    g.ab.base = aHi ? (long long)bfA * N + bfB : (long long)bfB * N + bfA;
+    g.ab.s0 = aHi ? N : 1; g.ab.s1 = aHi ? 1 : N;
+    g.cd.base = cHi ? (long long)bfC * N + bfD : (long long)bfD * N + bfC;
+    g.cd.s0 = cHi ? N : 1; g.cd.s1 = cHi ? 1 : N;
+    const int hiB = aHi ? bfA : bfB, hiK = cHi ? bfC : bfD;
+    const bool swapped = hiB < hiK;     // the template's bra pair is the canonical KET pair
+    auto cross = [&](int bfs, bool sHi, int bft, bool tHi, BlockAddr &p, BlockAddr &gg) {
+        // s from the template bra pair, t from the template ket pair
+        bool rowIsS;
+        if (!swapped) {
+            p.base = (long long)bfs * N + bft; p.s0 = N; p.s1 = 1;           // P[s,t]
+            rowIsS = !(!sHi && tHi);                                         // (lo bra, hi ket) stored as [t,s]
+        } else {
+            p.base = (long long)bft * N + bfs; p.s0 = 1; p.s1 = N;           // P[t,s]
+            rowIsS = (!tHi && sHi);                                          // normal [t,s]; exception (lo of canonical bra = t, hi of canonical ket = s)
+        }
+        if (rowIsS) { gg.base = (long long)bfs * N + bft; gg.s0 = N; gg.s1 = 1; }
+        else        { gg.base = (long long)bft * N + bfs; gg.s0 = 1; gg.s1 = N; }
+    };
+    cross(bfA, aHi, bfC, cHi, g.pac, g.gac);
+    cross(bfA, aHi, bfD, !cHi, g.pad, g.gad);
+    cross(bfB, !aHi, bfC, cHi, g.pbc, g.gbc);
+    cross(bfB, !aHi, bfD, !cHi, g.pbd, g.gbd);
+    return g;
+}
+
+template <int LA, int LB, int LC, int LD, int CD0, int NCDC>
+__device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestGeom &g, bool active, bool ket_uniform,
+                                             const double (&out)[ncart(LA) * ncart(LB) * NCDC])
+{
+    constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+    // which c / d components this chunk touches
+    auto need_c = [](int c) constexpr { for (int x = CD0; x < CD0 + NCDC; ++x) if (x / ND == c) return true; return false; };
+    auto need_d = [](int d) constexpr { for (int x = CD0; x < CD0 + NCDC; ++x) if (x % ND == d) return true; return false; };
+    const double *__restrict__ P = dg.dPre;
+    const double *__restrict__ SQ = dg.SQ;
+    double Jcd[NCDC];
+#pragma unroll
+    for (int x = 0; x < NCDC; ++x) Jcd[x] = 0.0;
+    if (active) {
+        double *__restrict__ G = dg.Gre;
+        const double tol = dg.tol;
+        // blocks that persist over the (a,b) loops: everything indexed by the ket shells only, or by b
+        double Pcd[NCDC], Qcd[NCDC], Pbc[NB * NC], Pbd[NB * ND], Kbc[NB * NC], Kbd[NB * ND];
+        sfor<0, NCDC>([&](auto I) {
+            constexpr int cdi = decltype(I)::value;
+            constexpr int cd = CD0 + cdi;
+            const long long o = g.cd.base + (cd / ND) * g.cd.s0 + (cd % ND) * g.cd.s1;
+            Pcd[cdi] = __ldg(&P[o]); Qcd[cdi] = __ldg(&SQ[o]);
+        });
+        sfor<0, NB>([&](auto B_) {
+            constexpr int b = decltype(B_)::value;
+            sfor<0, NC>([&](auto C_) {
+                constexpr int c = decltype(C_)::value;
+                if constexpr (need_c(c)) { Pbc[b * NC + c] = __ldg(&P[g.pbc.base + b * g.pbc.s0 + c * g.pbc.s1]); Kbc[b * NC + c] = 0.0; }
+            });
+            sfor<0, ND>([&](auto D_) {
+                constexpr int d = decltype(D_)::value;
+                if constexpr (need_d(d)) { Pbd[b * ND + d] = __ldg(&P[g.pbd.base + b * g.pbd.s0 + d * g.pbd.s1]); Kbd[b * ND + d] = 0.0; }
+            });
+        });
+        sfor<0, NA>([&](auto A_) {
+            constexpr int a = decltype(A_)::value;
+            double Pac[NC], Pad[ND], Kac[NC], Kad[ND];
+            sfor<0, NC>([&](auto C_) {
+                constexpr int c = decltype(C_)::value;
+                if constexpr (need_c(c)) { Pac[c] = __ldg(&P[g.pac.base + a * g.pac.s0 + c * g.pac.s1]); Kac[c] = 0.0; }
+            });
+            sfor<0, ND>([&](auto D_) {
+                constexpr int d = decltype(D_)::value;
+                if constexpr (need_d(d)) { Pad[d] = __ldg(&P[g.pad.base + a * g.pad.s0 + d * g.pad.s1]); Kad[d] = 0.0; }
+            });
+            sfor<0, NB>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                constexpr int ab = a * NB + b;
+                constexpr double sab = comp_scale(LA, a) * comp_scale(LB, b);
+                const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
+                const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
+                const double pab4 = 4.0 * fabs(pab);
+                double jab = 0.0;
+                sfor<0, NCDC>([&](auto J) {
+                    constexpr int cdi = decltype(J)::value;
+                    constexpr int cd = CD0 + cdi;
+                    constexpr int c = cd / ND, d = cd % ND;
+                    constexpr double s8 = 8.0 * sab * comp_scale(LC, c) * comp_scale(LD, d);
+                    double dmax = fmax(pab4, 4.0 * fabs(Pcd[cdi]));
+                    dmax = fmax(dmax, fmax(fmax(fabs(Pac[c]), fabs(Pad[d])), fmax(fabs(Pbc[b * NC + c]), fabs(Pbd[b * ND + d]))));
+                    const double bound = (qab * Qcd[cdi]) * dmax;
+                    const double e = (bound < tol) ? 0.0 : s8 * out[ab * NCDC + cdi];
+                    const double eq = -0.25 * e;
+                    jab = fma(Pcd[cdi], e, jab);
+                    Jcd[cdi] = fma(pab, e, Jcd[cdi]);
+                    Kac[c] = fma(Pbd[b * ND + d], eq, Kac[c]);
+                    Kbd[b * ND + d] = fma(Pac[c], eq, Kbd[b * ND + d]);
+                    Kad[d] = fma(Pbc[b * NC + c], eq, Kad[d]);
+                    Kbc[b * NC + c] = fma(Pad[d], eq, Kbc[b * NC + c]);
+                });
+                red_add_f64(&G[oab], jab);
+            });
+            sfor<0, NC>([&](auto C_) {
+                constexpr int c = decltype(C_)::value;
+                if constexpr (need_c(c)) red_add_f64(&G[g.gac.base + a * g.gac.s0 + c * g.gac.s1], Kac[c]);
+            });
+            sfor<0, ND>([&](auto D_) {
+                constexpr int d = decltype(D_)::value;
+                if constexpr (need_d(d)) red_add_f64(&G[g.gad.base + a * g.gad.s0 + d * g.gad.s1], Kad[d]);
+            });
+        });
+        sfor<0, NB>([&](auto B_) {
+            constexpr int b = decltype(B_)::value;
+            sfor<0, NC>([&](auto C_) {
+                constexpr int c = decltype(C_)::value;
+                if constexpr (need_c(c)) red_add_f64(&G[g.gbc.base + b * g.gbc.s0 + c * g.gbc.s1], Kbc[b * NC + c]);
+            });
+            sfor<0, ND>([&](auto D_) {
+                constexpr int d = decltype(D_)::value;
+                if constexpr (need_d(d)) red_add_f64(&G[g.gbd.base + b * g.gbd.s0 + d * g.gbd.s1], Kbd[b * ND + d]);
+            });
+        });
+    }
+    // J_cd: every lane of the warp works on the same ket pair in the common case -> one atomic per warp
+    if (ket_uniform) {
+        sfor<0, NCDC>([&](auto J) {
+            constexpr int cdi = decltype(J)::value;
+            double v = Jcd[cdi];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            Jcd[cdi] = v;
+        });
+        if ((threadIdx.x & 31) == 0) {
+            sfor<0, NCDC>([&](auto J) {
+                constexpr int cdi = decltype(J)::value;
+                constexpr int cd = CD0 + cdi;
+                red_add_f64(&dg.Gre[g.cd.base + (cd / ND) * g.cd.s0 + (cd % ND) * g.cd.s1], Jcd[cdi]);
+            });
+        }
+    } else if (active) {
+        sfor<0, NCDC>([&](auto J) {
+            constexpr int cdi = decltype(J)::value;
+            constexpr int cd = CD0 + cdi;
+            red_add_f64(&dg.Gre[g.cd.base + (cd / ND) * g.cd.s0 + (cd % ND) * g.cd.s1], Jcd[cdi]);
+        });
+    }
+}
+
+static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, const PairHdr &bh, const PairHdr &kh, bool samePair,
+                                               int la, int lb, int lc, int ld, int cd0, int ncdc, const double *vals)
+{
+    const int nb = ncart(lb), nd = ncart(ld), nab = ncart(la) * nb;
+    const bool sameAB = (bh.shA == bh.shB), sameCD = (kh.shA == kh.shB);
+    for (int ab = 0; ab < nab; ++ab) {
+        const int aa = ab / nb, bb = ab % nb;
+        const double sab = ((la == 2 && (aa == 0 || aa == 3 || aa == 5)) ? 0.57735026918962576451 : 1.0) *
+                           ((lb == 2 && (bb == 0 || bb == 3 || bb == 5)) ? 0.57735026918962576451 : 1.0);
+        for (int cdi = 0; cdi < ncdc; ++cdi) {
+            const int cd = cd0 + cdi, c = cd / nd, d = cd % nd;
+            const double s = sab * ((lc == 2 && (c == 0 || c == 3 || c == 5)) ? 0.57735026918962576451 : 1.0) *
+                             ((ld == 2 && (d == 0 || d == 3 || d == 5)) ? 0.57735026918962576451 : 1.0);
+            digest_fn_quartet(dg, bh.bfA + aa, bh.bfB + bb, kh.bfA + c, kh.bfB + d, sameAB, sameCD, samePair,
+                              vals[ab * ncdc + cdi] * s);
+        }
+    }
+}
+
 template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC>
-__device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, const PairHdr &bh, const PairHdr &kh,
-                                          const double *boys_tab, bool samePair)
+__device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, bool valid, const PairHdr &bh,
+                                          const PairHdr &kh, const double *boys_tab, bool samePair, bool fast,
+                                          bool ket_uniform)
 {
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND;
     double out[NAB * NCDC];
-    eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC>(bh, a.braP, kh, a.ketP, boys_tab, out);
+    if (valid) eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC>(bh, a.braP, kh, a.ketP, boys_tab, out);
     if constexpr (EPI == EPI_STORE) {
-        double *o = a.out + e * (unsigned long long)(NAB * NCD);
-        sfor<0, NAB>([&](auto ABI) {
-            constexpr int ab = decltype(ABI)::value;
-            constexpr double sab = comp_scale(LA, ab / NB) * comp_scale(LB, ab % NB);
-            sfor<0, NCDC>([&](auto CDI) {
-                constexpr int cdi = decltype(CDI)::value;
-                constexpr int cd = CD0 + cdi;
-                constexpr double s = sab * comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND);
-                o[ab * NCD + cd] = out[ab * NCDC + cdi] * s;
+        if (valid) {
+            double *o = a.out + e * (unsigned long long)(NAB * NCD);
+            sfor<0, NAB>([&](auto ABI) {
+                constexpr int ab = decltype(ABI)::value;
+                constexpr double sab = comp_scale(LA, ab / NB) * comp_scale(LB, ab % NB);
+                sfor<0, NCDC>([&](auto CDI) {
+                    constexpr int cdi = decltype(CDI)::value;
+                    constexpr int cd = CD0 + cdi;
+                    constexpr double s = sab * comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND);
+                    o[ab * NCD + cd] = out[ab * NCDC + cdi] * s;
+                });
             });
-        });
+        }
     } else {
-        const bool sameAB = (bh.shA == bh.shB), sameCD = (kh.shA == kh.shB);
-        sfor<0, NAB>([&](auto ABI) {
-            constexpr int ab = decltype(ABI)::value;
-            constexpr double sab = comp_scale(LA, ab / NB) * comp_scale(LB, ab % NB);
-            const int i = bh.bfA + ab / NB, j = bh.bfB + ab % NB;
-            sfor<0, NCDC>([&](auto CDI) {
-                constexpr int cdi = decltype(CDI)::value;
-                constexpr int cd = CD0 + cdi;
-                constexpr double s = sab * comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND);
-                digest_fn_quartet(a.dg, i, j, kh.bfA + cd / ND, kh.bfB + cd % ND, sameAB, sameCD, samePair,
-                                  out[ab * NCDC + cdi] * s);
-            });
-        });
+        // fast path participation is a per-lane property; the warp-level J_cd reduction inside runs for
+        // every lane (inactive lanes contribute zeros)
+        // block addresses are rebuilt here (a few integer ops) so they are not live across the ERI evaluation
+        const DigestGeom geom = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
+        digest_block<LA, LB, LC, LD, CD0, NCDC>(a.dg, geom, valid && fast, ket_uniform, out);
+        if (valid && !fast) {
+            // rare path (diagonal-type quartets, complex densities): runtime loops, kept out of line so the
+            // unrolled per-function code does not bloat the instruction footprint of the hot kernel
+            double tmp[NAB * NCDC];
+#pragma unroll
+            for (int x = 0; x < NAB * NCDC; ++x) tmp[x] = out[x];
+            digest_block_slow(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
+        }
     }
 }
 
 template <int LA, int LB, int LC, int LD, int EPI>
 __global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
 {
-    constexpr int L = LA + LB + LC + LD;
     constexpr int NCD = ncart(LC) * ncart(LD);
     constexpr int NCDC = chunk_ncd<LA, LB, LC, LD>();
     constexpr int NCHUNK = NCD / NCDC;
     extern __shared__ double s_boys[];
-    (void)L;
     for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = a.boys_tab[x];
     __syncthreads();
     const unsigned long long n = a.count_dev ? *a.count_dev : a.n;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-        const uint2 ij = a.list[e];
-        const PairHdr bh = a.braH[ij.x];
-        const PairHdr kh = a.ketH[ij.y];
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: every lane stays in the loop so the digestion can use warp shuffles
+    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
+        const unsigned long long e = base + lane;
+        const bool valid = e < n;
+        const uint2 ij = __ldg(a.list + (valid ? e : base));
+        const PairHdr bh = ld_hdr(a.braH + ij.x);
+        const PairHdr kh = ld_hdr(a.ketH + ij.y);
         const bool samePair = a.same_class && (ij.x == ij.y);
+        bool fast = false, ket_uniform = false;
+        if constexpr (EPI == EPI_DIGEST) {
+            const int hiB = max(bh.bfA, bh.bfB), hiK = max(kh.bfA, kh.bfB);
+            fast = (a.dg.dPim == nullptr) && (bh.shA != bh.shB) && (kh.shA != kh.shB) && (hiB != hiK);
+            const unsigned y0 = __shfl_sync(0xffffffffu, ij.y, 0);
+            // lanes off the fast path (or past the end) add zeros; the reduced J_cd goes to lane 0's ket pair
+            ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid) &&
+                          __shfl_sync(0xffffffffu, (int)fast, 0);
+        }
         sfor<0, NCHUNK>([&](auto CH) {
             constexpr int ch = decltype(CH)::value;
-            run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC>(a, e, bh, kh, s_boys, samePair);
+            run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC>(a, e, valid, bh, kh, s_boys, samePair, fast, ket_uniform);
         });
     }
 }

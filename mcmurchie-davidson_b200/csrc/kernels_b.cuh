@@ -5,6 +5,7 @@
 // intermediate are thread-local arrays with runtime indexing.
 #pragma once
 #include "core.cuh"
+#include "kernels_a.cuh"
 
 namespace mmdb {
 
@@ -96,13 +97,13 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
         const int c = cd / ND, d = cd % ND;
         const int cx = cart_pow_rt(lc, c, 0), cy = cart_pow_rt(lc, c, 1), cz = cart_pow_rt(lc, c, 2);
         const int dx = cart_pow_rt(ld, d, 0), dy = cart_pow_rt(ld, d, 1), dz = cart_pow_rt(ld, d, 2);
-        const uint2 ij = a.list[e];
-        const PairHdr bh = a.braH[ij.x];
-        const PairHdr kh = a.ketH[ij.y];
+        const uint2 ij = __ldg(a.list + e);
+        const PairHdr bh = ld_hdr(a.braH + ij.x);
+        const PairHdr kh = ld_hdr(a.ketH + ij.y);
         double out[36];
         for (int x = 0; x < NAB; ++x) out[x] = 0.0;
         for (int ib = 0; ib < bh.pnum; ++ib) {
-            const PrimPair b = a.braP[bh.poff + ib];
+            const PrimPair b = ld_prim(a.braP + bh.poff + ib);
             ETabRT Eb;
             {
                 const double PA[3] = {b.PAx, b.PAy, b.PAz};
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
             const int nhb = nherm(LBRA);
             for (int x = 0; x < nhb; ++x) G[x] = 0.0;
             for (int ik = 0; ik < kh.pnum; ++ik) {
-                const PrimPair k = a.ketP[kh.poff + ik];
+                const PrimPair k = ld_prim(a.ketP + kh.poff + ik);
                 const double pq = b.p + k.p, ipq = 1.0 / pq;
                 const double alpha = b.p * k.p * ipq;
                 const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
@@ -164,9 +165,58 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
         } else {
             const bool sameAB = (bh.shA == bh.shB), sameCD = (kh.shA == kh.shB);
             const bool samePair = a.same_class && (ij.x == ij.y);
-            for (int ab = 0; ab < NAB; ++ab)
-                digest_fn_quartet(a.dg, bh.bfA + ab / NB, bh.bfB + ab % NB, kh.bfA + c, kh.bfB + d, sameAB, sameCD,
-                                  samePair, out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB)));
+            const int hiB = max(bh.bfA, bh.bfB), hiK = max(kh.bfA, kh.bfB);
+            const bool fast = (a.dg.dPim == nullptr) && !sameAB && !sameCD && (hiB != hiK);
+            if (fast) {
+                // shell-level digestion for this thread's (c,d): see digest_block in kernels_a.cuh
+                const DigestGeom g = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
+                const double *__restrict__ P = a.dg.dPre;
+                const double *__restrict__ SQ = a.dg.SQ;
+                double *__restrict__ G = a.dg.Gre;
+                const double tol = a.dg.tol;
+                const long long ocd = g.cd.base + c * g.cd.s0 + d * g.cd.s1;
+                const double pcd = __ldg(&P[ocd]), qcd = __ldg(&SQ[ocd]), pcd4 = 4.0 * fabs(pcd);
+                double Pbc[6], Pbd[6], Kbc[6], Kbd[6];
+                for (int b = 0; b < NB; ++b) {
+                    Pbc[b] = __ldg(&P[g.pbc.base + b * g.pbc.s0 + c * g.pbc.s1]);
+                    Pbd[b] = __ldg(&P[g.pbd.base + b * g.pbd.s0 + d * g.pbd.s1]);
+                    Kbc[b] = 0.0; Kbd[b] = 0.0;
+                }
+                double jcd = 0.0;
+                for (int aa = 0; aa < NA; ++aa) {
+                    const double pac = __ldg(&P[g.pac.base + aa * g.pac.s0 + c * g.pac.s1]);
+                    const double pad = __ldg(&P[g.pad.base + aa * g.pad.s0 + d * g.pad.s1]);
+                    double kac = 0.0, kad = 0.0;
+                    for (int b = 0; b < NB; ++b) {
+                        const int ab = aa * NB + b;
+                        const long long oab = g.ab.base + aa * g.ab.s0 + b * g.ab.s1;
+                        const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
+                        double dmax = fmax(4.0 * fabs(pab), pcd4);
+                        dmax = fmax(dmax, fmax(fmax(fabs(pac), fabs(pad)), fmax(fabs(Pbc[b]), fabs(Pbd[b]))));
+                        const double bound = (qab * qcd) * dmax;
+                        const double sc = 8.0 * scd * comp_scale_rt(la, aa) * comp_scale_rt(lb, b);
+                        const double e = (bound < tol) ? 0.0 : sc * out[ab];
+                        const double eq = -0.25 * e;
+                        red_add_f64(&G[oab], pcd * e);
+                        jcd = fma(pab, e, jcd);
+                        kac = fma(Pbd[b], eq, kac);
+                        Kbd[b] = fma(pac, eq, Kbd[b]);
+                        kad = fma(Pbc[b], eq, kad);
+                        Kbc[b] = fma(pad, eq, Kbc[b]);
+                    }
+                    red_add_f64(&G[g.gac.base + aa * g.gac.s0 + c * g.gac.s1], kac);
+                    red_add_f64(&G[g.gad.base + aa * g.gad.s0 + d * g.gad.s1], kad);
+                }
+                for (int b = 0; b < NB; ++b) {
+                    red_add_f64(&G[g.gbc.base + b * g.gbc.s0 + c * g.gbc.s1], Kbc[b]);
+                    red_add_f64(&G[g.gbd.base + b * g.gbd.s0 + d * g.gbd.s1], Kbd[b]);
+                }
+                red_add_f64(&G[ocd], jcd);
+            } else {
+                for (int ab = 0; ab < NAB; ++ab)
+                    digest_fn_quartet(a.dg, bh.bfA + ab / NB, bh.bfB + ab % NB, kh.bfA + c, kh.bfB + d, sameAB, sameCD,
+                                      samePair, out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB)));
+            }
         }
     }
 }

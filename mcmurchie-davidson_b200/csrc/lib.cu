@@ -397,13 +397,17 @@ __global__ void dshell_kernel(const double *Dabs, int N, const int *bf0, const i
     }
 }
 
-// Shell-level screen -> compact quartet list.  One warp-wide ballot per 32 candidates.
-// Rows i in [row0,row1) with i % nshards == shard; candidates j < nket (j <= i when same_class).
+// Shell-level screen -> compact quartet list.
+// Rows are KET pairs j in [row0,row1) (j % nshards == shard), columns are BRA pairs i (i >= j when the
+// two classes coincide).  One block handles one row x 2048 consecutive columns: 8 candidates per thread,
+// block-wide prefix sum, ONE atomic per tile to reserve list space.  Entries of a row are written in
+// column order, so consecutive list entries share the ket pair (warp-uniform in the ERI kernels: the
+// inner primitive loop and the J_cd reduction run on broadcast data) and walk the bra pairs.
 struct ScreenArgs {
     const double *Qs_bra, *Qs_ket;
     const int2 *sh_bra, *sh_ket;
     const int *K_bra, *K_ket;
-    int nket, row0, row1, same_class, shard, nshards, nshell, all_pass;
+    int nbra, row0, row1, same_class, shard, nshards, nshell, all_pass;
     const double *DS;
     const unsigned long long *dglob;
     double tol;
@@ -411,64 +415,105 @@ struct ScreenArgs {
     unsigned long long *count, *primq, *cand;
 };
 
-__global__ void __launch_bounds__(256) screen_kernel(const ScreenArgs s)
+constexpr int SCR_THREADS = 256;
+constexpr int SCR_CPT = 8;
+constexpr int SCR_TILE = SCR_THREADS * SCR_CPT;
+
+__global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
 {
-    const int njb = (s.nket + 255) / 256;
-    const long long nblk = (long long)(s.row1 - s.row0) * njb;
-    const int lane = threadIdx.x & 31;
+    __shared__ unsigned s_wcnt[SCR_THREADS / 32];
+    __shared__ unsigned long long s_wk[SCR_THREADS / 32];
+    __shared__ unsigned s_wcand[SCR_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    const int ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
+    const long long nblk = (long long)(s.row1 - s.row0) * ntile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double dg4 = 0.0;
     if (!s.all_pass) dg4 = 4.0 * __longlong_as_double((long long)*s.dglob);
-    unsigned long long my_cand = 0;
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int i = s.row0 + (int)(blk / njb);
-        const int j = (int)(blk % njb) * 256 + threadIdx.x;
-        if (s.nshards > 1 && (i % s.nshards) != s.shard) continue;
-        const int jlim = s.same_class ? min(i + 1, s.nket) : s.nket;
-        if ((int)(blk % njb) * 256 >= jlim) continue;
-        bool pass = j < jlim;
+        const int j = s.row0 + (int)(blk / ntile);
+        const int c0 = (int)(blk % ntile) * SCR_TILE;
+        if (s.nshards > 1 && (j % s.nshards) != s.shard) continue;
+        const int cstart = s.same_class ? j : 0;
+        if (c0 + SCR_TILE <= cstart) continue;
+        const double qj = s.Qs_ket[j];
+        const int2 cd = s.sh_ket[j];
+        const unsigned long long kj = (unsigned long long)s.K_ket[j];
+        const int cbase = c0 + threadIdx.x * SCR_CPT;
+        unsigned bits = 0, ncand = 0;
         unsigned long long kk = 0;
-        if (pass) {
-            ++my_cand;
-            if (!s.all_pass) {
-                const double qq = s.Qs_bra[i] * s.Qs_ket[j];
-                pass = !(qq * dg4 < s.tol);
+#pragma unroll
+        for (int k = 0; k < SCR_CPT; ++k) {
+            const int i = cbase + k;
+            bool pass = (i < s.nbra) && (i >= cstart);
+            if (pass) {
+                ++ncand;
+                if (!s.all_pass) {
+                    const double qq = s.Qs_bra[i] * qj;
+                    pass = !(qq * dg4 < s.tol);
+                    if (pass) {
+                        const int2 ab = s.sh_bra[i];
+                        const double *DS = s.DS;
+                        const int ns = s.nshell;
+                        double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
+                        dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
+                                               fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
+                        pass = !(qq * dmax < s.tol);
+                    }
+                }
                 if (pass) {
-                    const int2 ab = s.sh_bra[i], cd = s.sh_ket[j];
-                    const double *DS = s.DS;
-                    const int ns = s.nshell;
-                    double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
-                    dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
-                                           fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
-                    pass = !(qq * dmax < s.tol);
+                    bits |= 1u << k;
+                    kk += (unsigned long long)s.K_bra[i] * kj;
                 }
             }
-            if (pass) kk = (unsigned long long)s.K_bra[i] * (unsigned long long)s.K_ket[j];
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            unsigned long long base = 0;
-            const int leader = __ffs(m) - 1;
-            // warp-level sum of primitive-quartet counts
-            unsigned long long ks = kk;
+        // block-wide exclusive scan of the survivor counts
+        const unsigned cnt = __popc(bits);
+        unsigned incl = cnt;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ks += __shfl_xor_sync(0xffffffffu, ks, o);
-            if (lane == leader) {
-                base = atomicAdd(s.count, (unsigned long long)__popc(m));
-                atomicAdd(s.primq, ks);
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        unsigned long long ks = kk;
+        unsigned cs = ncand;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ks += __shfl_xor_sync(0xffffffffu, ks, o);
+            cs += __shfl_xor_sync(0xffffffffu, cs, o);
+        }
+        if (lane == 31) s_wcnt[warp] = incl;
+        if (lane == 0) { s_wk[warp] = ks; s_wcand[warp] = cs; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0, tc = 0;
+            unsigned long long tk = 0;
+            for (int w = 0; w < SCR_THREADS / 32; ++w) {
+                const unsigned c = s_wcnt[w];
+                s_wcnt[w] = tot;
+                tot += c;
+                tk += s_wk[w];
+                tc += s_wcand[w];
             }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (pass) s.list[base + __popc(m & ((1u << lane) - 1))] = make_uint2((unsigned)i, (unsigned)j);
+            s_base = tot ? atomicAdd(s.count, (unsigned long long)tot) : 0ull;
+            if (tk) atomicAdd(s.primq, tk);
+            if (tc) atomicAdd(s.cand, (unsigned long long)tc);
         }
-    }
+        __syncthreads();
+        if (bits) {
+            unsigned long long pos = s_base + s_wcnt[warp] + (incl - cnt);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_cand += __shfl_xor_sync(0xffffffffu, my_cand, o);
-    if (lane == 0 && my_cand) atomicAdd(s.cand, my_cand);
+            for (int k = 0; k < SCR_CPT; ++k)
+                if (bits & (1u << k)) s.list[pos++] = make_uint2((unsigned)(cbase + k), (unsigned)j);
+        }
+        __syncthreads();
+    }
 }
 
 // scratch[entry][nfn] -> dense TwoE with all 8 images (cython/twoe.pyx:23-30)
 __global__ void scatter_dense_kernel(const uint2 *list, const unsigned long long *count, const PairHdr *braH,
-                                     const PairHdr *ketH, int la, int lb, int lc, int ld, const double *scratch,
-                                     int N, double *T)
+                                     const PairHdr *ketH, int la, int lb, int lc, int ld, int same_class,
+                                     const double *scratch, int N, double *T)
 {
     const int nb = ncart(lb), nc = ncart(lc), nd = ncart(ld);
     const int nfn = ncart(la) * nb * nc * nd;
@@ -485,6 +530,15 @@ __global__ void scatter_dense_kernel(const uint2 *list, const unsigned long long
         const uint2 ij = list[e];
         const PairHdr bh = braH[ij.x], kh = ketH[ij.y];
         const size_t i = bh.bfA + a, j = bh.bfB + bb, k = kh.bfA + c, l = kh.bfB + d;
+        // duplicates inside diagonal blocks ((a,b)/(b,a) of one shell, (ab|cd)/(cd|ab) of one pair) are
+        // evaluated by separate threads and may differ in the last bit: let exactly one of them write all
+        // eight images so the tensor is bit-symmetric like the reference's
+        if (bh.shA == bh.shB && i < j) continue;
+        if (kh.shA == kh.shB && k < l) continue;
+        if (same_class && ij.x == ij.y) {
+            const size_t hi1 = i > j ? i : j, lo1 = i > j ? j : i, hi2 = k > l ? k : l, lo2 = k > l ? l : k;
+            if (hi1 * (hi1 + 1) / 2 + lo1 < hi2 * (hi2 + 1) / 2 + lo2) continue;
+        }
         const double v = scratch[w];
         T[((i * n + j) * n + k) * n + l] = v;
         T[((k * n + l) * n + i) * n + j] = v;
@@ -555,14 +609,14 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
     ScreenArgs s;
     s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
     s.K_bra = B.K_dev; s.K_ket = K.K_dev;
-    s.nket = K.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
+    s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
     s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
     s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = b->list_dev;
     s.count = b->ctr_dev + 3 * slot; s.primq = b->ctr_dev + 3 * slot + 1; s.cand = b->ctr_dev + 3 * slot + 2;
-    const long long njb = (K.npairs + 255) / 256;
-    const long long nblk = (long long)(row1 - row0) * njb;
-    const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 64);
-    if (grid > 0) screen_kernel<<<grid, 256, 0, st>>>(s);
+    const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
+    const long long nblk = (long long)(row1 - row0) * ntile;
+    const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 32);
+    if (grid > 0) screen_kernel<<<grid, SCR_THREADS, 0, st>>>(s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MMDB_ERR_CUDA, std::string("screen kernel: ") + cudaGetErrorString(e));
     return MMDB_OK;
@@ -585,10 +639,10 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
             const size_t nfn = (size_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
-            size_t rows_per = std::max<size_t>(1, std::min(LIST_CAP, SCRATCH_CAP / nfn) / (size_t)K.npairs);
-            for (int row0 = 0; row0 < B.npairs; row0 += (int)rows_per) {
-                const int row1 = (int)std::min<size_t>(B.npairs, row0 + rows_per);
-                const size_t cap = (size_t)(row1 - row0) * K.npairs;
+            size_t rows_per = std::max<size_t>(1, std::min(LIST_CAP, SCRATCH_CAP / nfn) / (size_t)B.npairs);
+            for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
+                const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
+                const size_t cap = (size_t)(row1 - row0) * B.npairs;
                 CHK(ensure_list(b, cap));
                 CHK(ensure_scratch(b, cap * nfn));
                 if (slot * 3 + 2 >= b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
@@ -600,7 +654,7 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
                 a.same_class = (cb == ck);
                 CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, 0, st));
                 scatter_dense_kernel<<<b->nsm * 16, 256, 0, st>>>(b->list_dev, b->ctr_dev + 3 * slot, B.hdr_dev, K.hdr_dev,
-                                                                  B.la, B.lb, K.la, K.lb, b->scratch_dev, (int)N, TwoE_dev);
+                                                                  B.la, B.lb, K.la, K.lb, cb == ck ? 1 : 0, b->scratch_dev, (int)N, TwoE_dev);
                 ++slot;
             }
         }
@@ -636,10 +690,10 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         for (int ck = 0; ck <= cb; ++ck) {
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
-            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)K.npairs);
-            for (int row0 = 0; row0 < B.npairs; row0 += (int)rows_per) {
-                const int row1 = (int)std::min<size_t>(B.npairs, row0 + rows_per);
-                CHK(ensure_list(b, (size_t)(row1 - row0) * K.npairs));
+            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.npairs);
+            for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
+                const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
+                CHK(ensure_list(b, (size_t)(row1 - row0) * B.npairs));
                 if (slot * 3 + 2 >= b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
                 Launch ln{cb, ck, slot, nullptr, nullptr, nullptr};
                 if (timing) {
