@@ -251,8 +251,24 @@ __device__ __forceinline__ void build_E(ETab<LA, LB> &E, const double (&PA)[3], 
 // Fs[n] = prefactor * (-2 alpha)^n F_n(T) on entry.  Same branch order as the reference:
 // lower t if t > 0, else u if u > 0, else v.
 // ------------------------------------------------------------------------------------------
+template <int L, bool SMEM>
+struct RStore;
 template <int L>
-__device__ __forceinline__ void build_R(double (&R)[nherm(L)], const double (&Fs)[L + 1], double X, double Y, double Z)
+struct RStore<L, false> {          // registers
+    double v[nherm(L)];
+    __device__ __forceinline__ double &operator[](int i) { return v[i]; }
+    __device__ __forceinline__ const double &operator[](int i) const { return v[i]; }
+};
+template <int L>
+struct RStore<L, true> {           // shared memory, element i of thread tid at base[i * stride] (conflict-free)
+    double *base;
+    int stride;
+    __device__ __forceinline__ double &operator[](int i) { return base[i * stride]; }
+    __device__ __forceinline__ const double &operator[](int i) const { return base[i * stride]; }
+};
+
+template <int L, class RS>
+__device__ __forceinline__ void build_R_impl(RS &R, const double (&Fs)[L + 1], double X, double Y, double Z)
 {
     R[0] = Fs[L];
     sfor<0, L>([&](auto NN) {
@@ -283,14 +299,42 @@ __device__ __forceinline__ void build_R(double (&R)[nherm(L)], const double (&Fs
     });
 }
 
+// Boys + prefactor scaling + R recursion for one primitive quartet.
+template <int L, class RS>
+__device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, double cck, double X, double Y, double Z,
+                                       const double *__restrict__ boys_tab)
+{
+    const double pq = pb + pk;
+    const double ipq = 1.0 / pq;
+    const double alpha = pb * pk * ipq;
+    const double T = alpha * (X * X + Y * Y + Z * Z);
+    double Fs[L + 1];
+    boys_eval<L>(T, boys_tab, Fs);
+    double s = ccb * cck * sqrt(ipq);   // 2 pi^2.5 /(p q sqrt(p+q)) * c's * K's
+    const double m2a = -2.0 * alpha;
+#pragma unroll
+    for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
+    build_R_impl<L>(R, Fs, X, Y, Z);
+}
+
+// out-of-line copy for the shared-memory variant: the (long) recursion is emitted once per kernel
+// instead of once per ket-component chunk
+template <int L>
+__device__ __noinline__ void prim_R_smem(double *base, int stride, double pb, double pk, double ccb, double cck, double X,
+                                         double Y, double Z, const double *__restrict__ boys_tab)
+{
+    RStore<L, true> R{base, stride};
+    prim_R<L>(R, pb, pk, ccb, cck, X, Y, Z, boys_tab);
+}
+
 // ------------------------------------------------------------------------------------------
 // One contracted shell quartet, ket component pairs [CD0, CD0+NCDC), class-specialised.
 // out[ab*NCDC + cdi] accumulates (ab|cd) WITHOUT the per-component normalisation.
 // ------------------------------------------------------------------------------------------
-template <int LA, int LB, int LC, int LD, int CD0, int NCDC>
+template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM>
 __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const PrimPair *__restrict__ bp,
                                                    const PairHdr &kh, const PrimPair *__restrict__ kp,
-                                                   const double *__restrict__ boys_tab,
+                                                   const double *__restrict__ boys_tab, double *r_smem, int r_stride,
                                                    double (&out)[ncart(LA) * ncart(LB) * NCDC])
 {
     constexpr int LBRA = LA + LB, LKET = LC + LD, L = LBRA + LKET;
@@ -303,33 +347,24 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
 
     for (int ib = 0; ib < bh.pnum; ++ib) {
         const PrimPair b = ld_prim(bp + bh.poff + ib);
-        ETab<LA, LB> Eb;
-        {
-            const double PA[3] = {b.PAx, b.PAy, b.PAz};
-            const double PB[3] = {b.PAx + bh.ABx, b.PAy + bh.ABy, b.PAz + bh.ABz};
-            build_E<LA, LB>(Eb, PA, PB, 0.5 / b.p);
-        }
         double G[NHB * NCDC];
 #pragma unroll
         for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
 
         for (int ik = 0; ik < kh.pnum; ++ik) {
             const PrimPair k = ld_prim(kp + kh.poff + ik);
-            const double pq = b.p + k.p;
-            const double ipq = 1.0 / pq;
-            const double alpha = b.p * k.p * ipq;
             const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
-            const double T = alpha * (X * X + Y * Y + Z * Z);
-            double Fs[L + 1];
-            boys_eval<L>(T, boys_tab, Fs);
-            {
-                double s = b.cc * k.cc * sqrt(ipq);   // 2 pi^2.5 /(p q sqrt(p+q)) * c's * K's
-                const double m2a = -2.0 * alpha;
-#pragma unroll
-                for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
+            RStore<L, RSMEM> R;
+            if constexpr (RSMEM) {
+                R.base = r_smem;
+                R.stride = r_stride;
+                // a quartet with ONE primitive quartet keeps its R table in shared memory across the
+                // ket-component chunks: only the first chunk builds it
+                if (CD0 == 0 || bh.pnum * kh.pnum != 1)
+                    prim_R_smem<L>(r_smem, r_stride, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
+            } else {
+                prim_R<L>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
             }
-            double R[nherm(L)];
-            build_R<L>(R, Fs, X, Y, Z);
 
             ETab<LC, LD> Ek;
             {
@@ -370,6 +405,13 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
             });
         }
         // bra Hermite -> Cartesian:  out[ab][cd] += E^ab_t E^ab_u E^ab_v G[tuv][cd]
+        // (the bra E table is built here, after the ket primitives, so it is not live across the ket loop)
+        ETab<LA, LB> Eb;
+        {
+            const double PA[3] = {b.PAx, b.PAy, b.PAz};
+            const double PB[3] = {b.PAx + bh.ABx, b.PAy + bh.ABy, b.PAz + bh.ABz};
+            build_E<LA, LB>(Eb, PA, PB, 0.5 / b.p);
+        }
         sfor<0, NAB>([&](auto ABI) {
             constexpr int ab = decltype(ABI)::value;
             constexpr int a = ab / NB, bb = ab % NB;

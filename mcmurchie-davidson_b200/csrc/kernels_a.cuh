@@ -9,15 +9,45 @@ namespace mmdb {
 
 constexpr int KA_THREADS = 128;
 
+__host__ __device__ constexpr int etab_size(int la, int lb)
+{
+    int n = 0;
+    for (int i = 0; i <= la; ++i)
+        for (int j = 0; j <= lb; ++j) n += i + j + 1;
+    return n;
+}
+
+// R_tuv lives in shared memory (one column per thread) for the high-L classes, in registers otherwise
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr bool r_in_smem()
+{
+    return LA + LB + LC + LD >= 5;
+}
+
 // ket component pairs per chunk
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr int chunk_ncd()
 {
     constexpr int NAB = ncart(LA) * ncart(LB), NCD = ncart(LC) * ncart(LD), NHB = nherm(LA + LB);
     int best = 1;
-    for (int c = 1; c <= NCD; ++c)
-        if (NCD % c == 0 && NAB * c <= 36 && NHB * c <= 40) best = c;
+    if (r_in_smem<LA, LB, LC, LD>()) {
+        // live doubles: ket transform G + ket E table; bra transform G + out + bra E table
+        constexpr int nEb = 3 * etab_size(LA, LB), nEk = 3 * etab_size(LC, LD);
+        for (int c = 1; c <= NCD; ++c)
+            if (NCD % c == 0 && NHB * c + nEk <= 112 && (NAB + NHB) * c + nEb <= 124) best = c;
+    } else {
+        for (int c = 1; c <= NCD; ++c)
+            if (NCD % c == 0 && NAB * c <= 36 && NHB * c <= 40) best = c;
+    }
     return best;
+}
+
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr size_t class_smem_bytes()
+{
+    size_t b = (size_t)BOYS_ROWS * BOYS_STRIDE * sizeof(double);
+    if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(LA + LB + LC + LD) * KA_THREADS * sizeof(double);
+    return b;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -217,7 +247,10 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND;
     double out[NAB * NCDC];
-    if (valid) eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC>(bh, a.braP, kh, a.ketP, boys_tab, out);
+    if (valid)
+        eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>()>(
+            bh, a.braP, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + BOYS_ROWS * BOYS_STRIDE + threadIdx.x,
+            KA_THREADS, out);
     if constexpr (EPI == EPI_STORE) {
         if (valid) {
             double *o = a.out + e * (unsigned long long)(NAB * NCD);
@@ -292,7 +325,15 @@ cudaError_t launch_class(const EriArgs &a, int epi, int grid, cudaStream_t st);
 template <int LA, int LB, int LC, int LD>
 cudaError_t launch_class_impl(const EriArgs &a, int epi, int grid, cudaStream_t st)
 {
-    const size_t smem = BOYS_ROWS * BOYS_STRIDE * sizeof(double);
+    constexpr size_t smem = class_smem_bytes<LA, LB, LC, LD>();
+    if (smem > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = true;
+        }
+    }
     if (epi == EPI_STORE)
         eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<grid, KA_THREADS, smem, st>>>(a);
     else

@@ -300,10 +300,13 @@ DECL(0, 0, 0, 0) DECL(1, 0, 0, 0) DECL(1, 0, 1, 0) DECL(1, 1, 0, 0) DECL(1, 1, 1
 DECL(2, 0, 0, 0) DECL(2, 0, 1, 0) DECL(2, 0, 1, 1) DECL(2, 0, 2, 0)
 DECL(2, 1, 0, 0) DECL(2, 1, 1, 0) DECL(2, 1, 1, 1) DECL(2, 1, 2, 0)
 DECL(2, 2, 0, 0) DECL(2, 2, 1, 0)
+DECL(2, 1, 2, 1) DECL(2, 2, 1, 1) DECL(2, 2, 2, 0) DECL(2, 2, 2, 1)
 #undef DECL
 }  // namespace mmdb
 
-static bool has_class_kernel(int la, int lb, int lc, int ld) { return la + lb + lc + ld <= 5; }
+// every class except (dd|dd) has a class-specialised kernel; (dd|dd) (a few thousand quartets, minutes of
+// compile time when fully unrolled) runs on the generic runtime-L kernel
+static bool has_class_kernel(int la, int lb, int lc, int ld) { return la + lb + lc + ld <= 7; }
 
 // (la lb) >= (lc ld) in pair-class order is required
 static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a, int epi, int impl, cudaStream_t st)
@@ -323,6 +326,7 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
             CASE(2, 0, 0, 0) CASE(2, 0, 1, 0) CASE(2, 0, 1, 1) CASE(2, 0, 2, 0)
             CASE(2, 1, 0, 0) CASE(2, 1, 1, 0) CASE(2, 1, 1, 1) CASE(2, 1, 2, 0)
             CASE(2, 2, 0, 0) CASE(2, 2, 1, 0)
+            CASE(2, 1, 2, 1) CASE(2, 2, 1, 1) CASE(2, 2, 2, 0) CASE(2, 2, 2, 1)
 #undef CASE
             default:
                 return fail(MMDB_ERR_INVALID, "launch_eri: class not instantiated");
