@@ -293,10 +293,13 @@ __global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
     __syncthreads();
     const unsigned long long n = a.count_dev ? *a.count_dev : a.n;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    // warp-uniform trip count: every lane stays in the loop so the digestion can use warp shuffles
-    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
-        const unsigned long long e = base + lane;
+    // Block-uniform trip count: every warp stays in the loop (the digestion uses warp shuffles) and, for the
+    // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
+    // barrier per quartet so they stream through the code together (one fetch serves all of them).
+    constexpr bool LOCKSTEP = (LA + LB + LC + LD >= 3);
+    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < n; base += stride) {
+        if constexpr (LOCKSTEP) __syncthreads();
+        const unsigned long long e = base + threadIdx.x;
         const bool valid = e < n;
         const uint2 ij = __ldg(a.list + (valid ? e : base));
         const PairHdr bh = ld_hdr(a.braH + ij.x);
@@ -334,10 +337,18 @@ cudaError_t launch_class_impl(const EriArgs &a, int epi, int grid, cudaStream_t 
             configured = true;
         }
     }
+    // persistent grid: as many CTAs as are co-resident (occupancy x SM count); `grid` carries the SM count
+    static int occ_store = 0, occ_digest = 0;
+    if (occ_store == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_store, eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, KA_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_digest, eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, KA_THREADS, smem);
+        if (occ_store < 1) occ_store = 1;
+        if (occ_digest < 1) occ_digest = 1;
+    }
     if (epi == EPI_STORE)
-        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<grid, KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<grid * occ_store, KA_THREADS, smem, st>>>(a);
     else
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<grid, KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<grid * occ_digest, KA_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -315,7 +315,7 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
     a.boys_tab = b->boys_dev[L];
     const int key = ((la * 3 + lb) * 3 + lc) * 3 + ld;
     cudaError_t e = cudaSuccess;
-    const int gridA = b->nsm * 8;
+    const int gridA = b->nsm;   // x occupancy inside launch_class
     if (impl == 0 && has_class_kernel(la, lb, lc, ld)) {
         switch (key) {
 #define CASE(LA, LB, LC, LD)                                  \
