@@ -195,6 +195,54 @@ def main_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------
+# in-core leg: benzene/6-31G** (N = 120, TwoE = 1.66 GB resident in HBM)
+# ------------------------------------------------------------------------------------------------
+def incore_bench(E, L, synth, Molecule, np, torch, C):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    mol = Molecule(*synth.config("benzene_631gss"))
+    eng = mol.engine
+    N = mol.nbasis
+    dev = eng.tdev
+    T = torch.empty((N, N, N, N), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            fn()
+            e1.record(st)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    fill_ms = timed(lambda: L.check(eng.lib.mmdb_eri_dense(eng.h, L.ptr(T), C.c_void_p(st.cuda_stream))), 3)
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((N, N))
+    P = torch.from_numpy(np.ascontiguousarray(A + A.T)).to(dev)
+    out = torch.empty((2, N, N), dtype=torch.float64, device=dev)
+    jk_ms = timed(lambda: L.check(eng.lib.mmdb_jk_incore(eng.device, L.ptr(T), N, L.ptr(P), None, L.ptr(out[0]), None,
+                                                         L.ptr(out[1]), None, C.c_void_p(st.cuda_stream))), 10)
+    bytes_alg = 8.0 * N ** 4 + 4 * 8.0 * N * N
+    ach = bytes_alg / (jk_ms * 1e-3) / 1e9
+    nuniq = (N * (N + 1) // 2) * (N * (N + 1) // 2 + 1) // 2
+    return {"workload": "benzene_631gss in-core, N=%d, TwoE %.2f GB (tensor larger than L2)" % (N, 8.0 * N ** 4 / 1e9),
+            "dense_fill_ms": fill_ms, "unique_integrals_per_s": nuniq / (fill_ms * 1e-3),
+            "jk_ms": jk_ms, "fock_builds_per_s": 1e3 / jk_ms,
+            "roofline": {"bound": "hbm", "kernel": "jk_incore_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def main_ours(a):
@@ -328,6 +376,12 @@ def main_ours(a):
                             "screen_ms": round(v["screen_ms"], 4),
                             "tflops": v["prim_quartets"] * v["flops_per_prim_quartet"] / max(v["ms"], 1e-9) / 1e9}
                         for k, v in st["classes"].items()} if a.class_timing else None}
+    # ---- in-core path (config 2: benzene/6-31G**): dense fill + one-pass J/K, HBM roofline ----------
+    if world == 1:
+        try:
+            line["incore_config2"] = incore_bench(E, L, synth, Molecule, np, torch, C)
+        except Exception as exc:      # the direct-build line must not be lost to an in-core failure
+            line["incore_config2"] = {"error": str(exc)[:200]}
     # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
     if world == 1 and a.cpu_baseline:
         sample = load_sample(a.workload)

@@ -94,6 +94,10 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
 {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
+}
 __device__ __forceinline__ PrimPair ld_prim(const PrimPair *p)
 {
     const double2 *q = reinterpret_cast<const double2 *>(p);

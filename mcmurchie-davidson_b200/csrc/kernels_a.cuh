@@ -297,13 +297,24 @@ __global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
     // barrier per quartet so they stream through the code together (one fetch serves all of them).
     constexpr bool LOCKSTEP = (LA + LB + LC + LD >= 3);
-    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < n; base += stride) {
+    // software pipeline over the quartet list: the list entry is read one iteration ahead and the pair
+    // headers + first primitive pairs of the NEXT quartet are prefetched into L1 while this one is computed
+    unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x;
+    uint2 ij_next = make_uint2(0u, 0u);
+    if (base < n) ij_next = __ldg(a.list + min(base + threadIdx.x, n - 1));
+    for (; base < n; base += stride) {
         if constexpr (LOCKSTEP) __syncthreads();
         const unsigned long long e = base + threadIdx.x;
         const bool valid = e < n;
-        const uint2 ij = __ldg(a.list + (valid ? e : base));
+        const uint2 ij = ij_next;
         const PairHdr bh = ld_hdr(a.braH + ij.x);
         const PairHdr kh = ld_hdr(a.ketH + ij.y);
+        if (base + stride < n) {
+            ij_next = __ldg(a.list + min(e + stride, n - 1));
+            prefetch_l1(a.braH + ij_next.x);
+            prefetch_l1(a.ketH + ij_next.y);
+        }
+        prefetch_l1(a.braP + bh.poff);
         const bool samePair = a.same_class && (ij.x == ij.y);
         bool fast = false, ket_uniform = false;
         if constexpr (EPI == EPI_DIGEST) {
