@@ -503,7 +503,8 @@ struct EriArgs {
     const PrimPair *braP;
     const PairHdr *ketH;
     const PrimPair *ketP;
-    const uint2 *list;            // (bra pair, ket pair) per entry
+    const uint2 *list;            // (bra pair, ket pair) per entry; entry e lives at list[e * list_step]
+    long long list_step;          // +1: front-to-back (fast-path list), -1: back-to-front (slow-path list)
     const unsigned long long *count_dev;   // number of entries (device) or nullptr -> use n
     unsigned long long n;
     const double *boys_tab;       // [BOYS_ROWS][BOYS_STRIDE] for this class's L (global)
@@ -512,6 +513,8 @@ struct EriArgs {
     DigestArgs dg;                // EPI_DIGEST
 };
 
-enum { EPI_STORE = 0, EPI_DIGEST = 1 };
+// EPI_DIGEST: every entry satisfies the block-digestion preconditions (the screening kernel sorts the
+// others into a second list); EPI_DIGEST_SLOW: per-function digestion for that second list
+enum { EPI_STORE = 0, EPI_DIGEST = 1, EPI_DIGEST_SLOW = 2 };
 
 }  // namespace mmdb

@@ -241,8 +241,7 @@ static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, cons
 
 template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC>
 __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, bool valid, const PairHdr &bh,
-                                          const PairHdr &kh, const double *boys_tab, bool samePair, bool fast,
-                                          bool ket_uniform)
+                                          const PairHdr &kh, const double *boys_tab, bool samePair, bool ket_uniform)
 {
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND;
@@ -265,15 +264,14 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
                 });
             });
         }
-    } else {
-        // fast path participation is a per-lane property; the warp-level J_cd reduction inside runs for
-        // every lane (inactive lanes contribute zeros)
-        // block addresses are rebuilt here (a few integer ops) so they are not live across the ERI evaluation
+    } else if constexpr (EPI == EPI_DIGEST) {
+        // block addresses are rebuilt here (a few integer ops) so they are not live across the ERI evaluation;
+        // the warp-level J_cd reduction inside runs for every lane (inactive lanes contribute zeros)
         const DigestGeom geom = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
-        digest_block<LA, LB, LC, LD, CD0, NCDC>(a.dg, geom, valid && fast, ket_uniform, out);
-        if (valid && !fast) {
-            // rare path (diagonal-type quartets, complex densities): runtime loops, kept out of line so the
-            // unrolled per-function code does not bloat the instruction footprint of the hot kernel
+        digest_block<LA, LB, LC, LD, CD0, NCDC>(a.dg, geom, valid, ket_uniform, out);
+    } else {
+        // second list (diagonal-type quartets, complex densities): per-function digestion, out of line
+        if (valid) {
             double tmp[NAB * NCDC];
 #pragma unroll
             for (int x = 0; x < NAB * NCDC; ++x) tmp[x] = out[x];
@@ -297,11 +295,11 @@ __global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
     // barrier per quartet so they stream through the code together (one fetch serves all of them).
     constexpr bool LOCKSTEP = (LA + LB + LC + LD >= 3);
-    // software pipeline over the quartet list: the list entry is read one iteration ahead and the pair
-    // headers + first primitive pairs of the NEXT quartet are prefetched into L1 while this one is computed
+    // the list entry of the NEXT quartet is read one iteration ahead
     unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x;
+    const long long lstep = a.list_step;
     uint2 ij_next = make_uint2(0u, 0u);
-    if (base < n) ij_next = __ldg(a.list + min(base + threadIdx.x, n - 1));
+    if (base < n) ij_next = __ldg(a.list + (long long)min(base + threadIdx.x, n - 1) * lstep);
     for (; base < n; base += stride) {
         if constexpr (LOCKSTEP) __syncthreads();
         const unsigned long long e = base + threadIdx.x;
@@ -309,25 +307,16 @@ __global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
         const uint2 ij = ij_next;
         const PairHdr bh = ld_hdr(a.braH + ij.x);
         const PairHdr kh = ld_hdr(a.ketH + ij.y);
-        if (base + stride < n) {
-            ij_next = __ldg(a.list + min(e + stride, n - 1));
-            prefetch_l1(a.braH + ij_next.x);
-            prefetch_l1(a.ketH + ij_next.y);
-        }
-        prefetch_l1(a.braP + bh.poff);
+        if (base + stride < n) ij_next = __ldg(a.list + (long long)min(e + stride, n - 1) * lstep);
         const bool samePair = a.same_class && (ij.x == ij.y);
-        bool fast = false, ket_uniform = false;
+        bool ket_uniform = false;
         if constexpr (EPI == EPI_DIGEST) {
-            const int hiB = max(bh.bfA, bh.bfB), hiK = max(kh.bfA, kh.bfB);
-            fast = (a.dg.dPim == nullptr) && (bh.shA != bh.shB) && (kh.shA != kh.shB) && (hiB != hiK);
             const unsigned y0 = __shfl_sync(0xffffffffu, ij.y, 0);
-            // lanes off the fast path (or past the end) add zeros; the reduced J_cd goes to lane 0's ket pair
-            ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid) &&
-                          __shfl_sync(0xffffffffu, (int)fast, 0);
+            ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid);
         }
         sfor<0, NCHUNK>([&](auto CH) {
             constexpr int ch = decltype(CH)::value;
-            run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC>(a, e, valid, bh, kh, s_boys, samePair, fast, ket_uniform);
+            run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform);
         });
     }
 }
@@ -340,26 +329,26 @@ template <int LA, int LB, int LC, int LD>
 cudaError_t launch_class_impl(const EriArgs &a, int epi, int grid, cudaStream_t st)
 {
     constexpr size_t smem = class_smem_bytes<LA, LB, LC, LD>();
-    if (smem > 48 * 1024) {
-        static bool configured = false;
-        if (!configured) {
+    static int occ[3] = {0, 0, 0};
+    if (occ[0] == 0) {
+        if (smem > 48 * 1024) {
             cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = true;
+            cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-    }
-    // persistent grid: as many CTAs as are co-resident (occupancy x SM count); `grid` carries the SM count
-    static int occ_store = 0, occ_digest = 0;
-    if (occ_store == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_store, eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, KA_THREADS, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_digest, eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, KA_THREADS, smem);
-        if (occ_store < 1) occ_store = 1;
-        if (occ_digest < 1) occ_digest = 1;
+        // persistent grid: as many CTAs as are co-resident (occupancy x SM count); `grid` carries the SM count
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, KA_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, KA_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, KA_THREADS, smem);
+        for (int &o : occ)
+            if (o < 1) o = 1;
     }
     if (epi == EPI_STORE)
-        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<grid * occ_store, KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<grid * occ[0], KA_THREADS, smem, st>>>(a);
+    else if (epi == EPI_DIGEST)
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<grid * occ[1], KA_THREADS, smem, st>>>(a);
     else
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<grid * occ_digest, KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW><<<grid * occ[2], KA_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

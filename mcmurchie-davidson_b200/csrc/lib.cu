@@ -336,7 +336,7 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
         const int grid = b->nsm * 8;
         if (epi == EPI_STORE)
             eri_generic_kernel<EPI_STORE><<<grid, KB_THREADS, smem, st>>>(a, la, lb, lc, ld);
-        else
+        else   // the generic kernel decides block / per-function digestion per quartet, so it serves both lists
             eri_generic_kernel<EPI_DIGEST><<<grid, KB_THREADS, smem, st>>>(a, la, lb, lc, ld);
         e = cudaGetLastError();
     }
@@ -412,6 +412,11 @@ struct ScreenArgs {
     const int2 *sh_bra, *sh_ket;
     const int *K_bra, *K_ket;
     int nbra, row0, row1, same_class, shard, nshards, nshell, all_pass;
+    int split;                     // classify survivors: block-digestible entries front-to-back, the rest back-to-front
+    int force_slow;                // complex density: everything goes to the second list
+    const int *bf0;                // first function index per shell
+    long long cap;                 // list capacity (the slow list starts at list[cap-1] and grows downwards)
+    unsigned long long *count_slow;
     const double *DS;
     const unsigned long long *dglob;
     double tol;
@@ -425,10 +430,10 @@ constexpr int SCR_TILE = SCR_THREADS * SCR_CPT;
 
 __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
 {
-    __shared__ unsigned s_wcnt[SCR_THREADS / 32];
+    __shared__ unsigned long long s_wcnt[SCR_THREADS / 32];
     __shared__ unsigned long long s_wk[SCR_THREADS / 32];
     __shared__ unsigned s_wcand[SCR_THREADS / 32];
-    __shared__ unsigned long long s_base;
+    __shared__ unsigned long long s_base, s_base_slow;
     const int ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(s.row1 - s.row0) * ntile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -444,19 +449,22 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const int2 cd = s.sh_ket[j];
         const unsigned long long kj = (unsigned long long)s.K_ket[j];
         const int cbase = c0 + threadIdx.x * SCR_CPT;
-        unsigned bits = 0, ncand = 0;
+        unsigned bits = 0, sbits = 0, ncand = 0;
         unsigned long long kk = 0;
+        const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
+        const bool ketDiag = cd.x == cd.y;
 #pragma unroll
         for (int k = 0; k < SCR_CPT; ++k) {
             const int i = cbase + k;
             bool pass = (i < s.nbra) && (i >= cstart);
             if (pass) {
                 ++ncand;
+                int2 ab = make_int2(0, 0);
                 if (!s.all_pass) {
                     const double qq = s.Qs_bra[i] * qj;
                     pass = !(qq * dg4 < s.tol);
                     if (pass) {
-                        const int2 ab = s.sh_bra[i];
+                        ab = s.sh_bra[i];
                         const double *DS = s.DS;
                         const int ns = s.nshell;
                         double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
@@ -468,15 +476,21 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                 if (pass) {
                     bits |= 1u << k;
                     kk += (unsigned long long)s.K_bra[i] * kj;
+                    if (s.split) {
+                        // block digestion needs A != B, C != D and different leading shells (kernels_a.cuh)
+                        const bool slow = s.force_slow || ketDiag || ab.x == ab.y || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
+                        if (slow) sbits |= 1u << k;
+                    }
                 }
             }
         }
-        // block-wide exclusive scan of the survivor counts
-        const unsigned cnt = __popc(bits);
-        unsigned incl = cnt;
+        // block-wide exclusive scan of the survivor counts (fast list in the low half, slow list in the high half)
+        const unsigned nslow = __popc(sbits), cnt = __popc(bits) - nslow;
+        unsigned long long incl = (unsigned long long)cnt | ((unsigned long long)nslow << 32);
+        const unsigned long long mine = incl;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
         unsigned long long ks = kk;
@@ -490,25 +504,33 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         if (lane == 0) { s_wk[warp] = ks; s_wcand[warp] = cs; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned tot = 0, tc = 0;
-            unsigned long long tk = 0;
+            unsigned long long tot = 0, tk = 0;
+            unsigned tc = 0;
             for (int w = 0; w < SCR_THREADS / 32; ++w) {
-                const unsigned c = s_wcnt[w];
+                const unsigned long long c = s_wcnt[w];
                 s_wcnt[w] = tot;
                 tot += c;
                 tk += s_wk[w];
                 tc += s_wcand[w];
             }
-            s_base = tot ? atomicAdd(s.count, (unsigned long long)tot) : 0ull;
+            const unsigned tf = (unsigned)(tot & 0xffffffffull), tsl = (unsigned)(tot >> 32);
+            s_base = tf ? atomicAdd(s.count, (unsigned long long)tf) : 0ull;
+            s_base_slow = tsl ? atomicAdd(s.count_slow, (unsigned long long)tsl) : 0ull;
             if (tk) atomicAdd(s.primq, tk);
             if (tc) atomicAdd(s.cand, (unsigned long long)tc);
         }
         __syncthreads();
         if (bits) {
-            unsigned long long pos = s_base + s_wcnt[warp] + (incl - cnt);
+            const unsigned long long excl = s_wcnt[warp] + (incl - mine);
+            long long pos = (long long)(s_base + (excl & 0xffffffffull));
+            long long spos = s.cap - 1 - (long long)(s_base_slow + (excl >> 32));
 #pragma unroll
             for (int k = 0; k < SCR_CPT; ++k)
-                if (bits & (1u << k)) s.list[pos++] = make_uint2((unsigned)(cbase + k), (unsigned)j);
+                if (bits & (1u << k)) {
+                    const uint2 ent = make_uint2((unsigned)(cbase + k), (unsigned)j);
+                    if (sbits & (1u << k)) s.list[spos--] = ent;
+                    else s.list[pos++] = ent;
+                }
         }
         __syncthreads();
     }
@@ -573,7 +595,7 @@ extern "C" int mmdb_eri_shell_quartets(mmdb_basis *b, int pc_bra, int pc_ket, in
     EriArgs a;
     std::memset(&a, 0, sizeof(a));
     a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
-    a.list = b->list_dev; a.count_dev = nullptr; a.n = (unsigned long long)n; a.out = out_dev;
+    a.list = b->list_dev; a.list_step = 1; a.count_dev = nullptr; a.n = (unsigned long long)n; a.out = out_dev;
     a.same_class = (pc_bra == pc_ket);
     return launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, impl, st);
 }
@@ -596,7 +618,7 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
         EriArgs a;
         std::memset(&a, 0, sizeof(a));
         a.braH = P.hdr_dev; a.braP = P.prim_dev; a.ketH = P.hdr_dev; a.ketP = P.prim_dev;
-        a.list = b->list_dev; a.n = (unsigned long long)P.npairs; a.out = b->scratch_dev; a.same_class = 1;
+        a.list = b->list_dev; a.list_step = 1; a.n = (unsigned long long)P.npairs; a.out = b->scratch_dev; a.same_class = 1;
         CHK(launch_eri(b, P.la, P.lb, P.la, P.lb, a, EPI_STORE, 0, st));
         schwarz_extract_kernel<<<(P.npairs + 127) / 128, 128, 0, st>>>(P.hdr_dev, P.npairs, P.la, P.lb, b->scratch_dev,
                                                                        b->nbf, b->Q_dev, b->SQ_dev, P.Qs_dev);
@@ -607,8 +629,10 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
     return MMDB_OK;
 }
 
+constexpr int CTR_PER_LAUNCH = 4;   // survivors (fast list), primitive quartets, candidates, survivors (slow list)
+
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
-                      bool all_pass, double tol, int slot, cudaStream_t st)
+                      bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, cudaStream_t st)
 {
     ScreenArgs s;
     s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
@@ -616,7 +640,8 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
     s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
     s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
     s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = b->list_dev;
-    s.count = b->ctr_dev + 3 * slot; s.primq = b->ctr_dev + 3 * slot + 1; s.cand = b->ctr_dev + 3 * slot + 2;
+    s.count = b->ctr_dev + CTR_PER_LAUNCH * slot; s.primq = s.count + 1; s.cand = s.count + 2; s.count_slow = s.count + 3;
+    s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
     const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(row1 - row0) * ntile;
     const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 32);
@@ -649,15 +674,15 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
                 const size_t cap = (size_t)(row1 - row0) * B.npairs;
                 CHK(ensure_list(b, cap));
                 CHK(ensure_scratch(b, cap * nfn));
-                if (slot * 3 + 2 >= b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
-                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, st));
+                if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
+                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, st));
                 EriArgs a;
                 std::memset(&a, 0, sizeof(a));
                 a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
-                a.list = b->list_dev; a.count_dev = b->ctr_dev + 3 * slot; a.out = b->scratch_dev;
+                a.list = b->list_dev; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.out = b->scratch_dev;
                 a.same_class = (cb == ck);
                 CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, 0, st));
-                scatter_dense_kernel<<<b->nsm * 16, 256, 0, st>>>(b->list_dev, b->ctr_dev + 3 * slot, B.hdr_dev, K.hdr_dev,
+                scatter_dense_kernel<<<b->nsm * 16, 256, 0, st>>>(b->list_dev, b->ctr_dev + CTR_PER_LAUNCH * slot, B.hdr_dev, K.hdr_dev,
                                                                   B.la, B.lb, K.la, K.lb, cb == ck ? 1 : 0, b->scratch_dev, (int)N, TwoE_dev);
                 ++slot;
             }
@@ -697,8 +722,9 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.npairs);
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                CHK(ensure_list(b, (size_t)(row1 - row0) * B.npairs));
-                if (slot * 3 + 2 >= b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
+                const size_t cap = (size_t)(row1 - row0) * B.npairs;
+                CHK(ensure_list(b, cap));
+                if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
                 Launch ln{cb, ck, slot, nullptr, nullptr, nullptr};
                 if (timing) {
                     CU(cudaEventCreate(&ln.e0));
@@ -706,30 +732,36 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                     CU(cudaEventCreate(&ln.e1));
                     CU(cudaEventRecord(ln.e0, st));
                 }
-                CHK(run_screen(b, B, K, cb == ck, row0, row1, shard, nshards, false, tol, slot, st));
+                CHK(run_screen(b, B, K, cb == ck, row0, row1, shard, nshards, false, tol, slot, true, dP_im_dev != nullptr,
+                               (long long)cap, st));
                 if (timing) CU(cudaEventRecord(ln.em, st));
                 EriArgs a;
                 std::memset(&a, 0, sizeof(a));
                 a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
-                a.list = b->list_dev; a.count_dev = b->ctr_dev + 3 * slot; a.same_class = (cb == ck);
+                a.list = b->list_dev; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.same_class = (cb == ck);
                 a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
                 a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
+                // block-digestible quartets, then the second list (diagonal-type quartets / complex density)
                 CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST, 0, st));
+                a.list = b->list_dev + (cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + 3;
+                CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST_SLOW, 0, st));
                 if (timing) CU(cudaEventRecord(ln.e1, st));
                 launches.push_back(ln);
                 ++slot;
             }
         }
     if (stats) {
-        std::vector<unsigned long long> ctr(3 * (size_t)slot + 3, 0ull);
-        CU(cudaMemcpyAsync(ctr.data(), b->ctr_dev, sizeof(unsigned long long) * 3 * slot, cudaMemcpyDeviceToHost, st));
+        std::vector<unsigned long long> ctr(CTR_PER_LAUNCH * (size_t)slot + CTR_PER_LAUNCH, 0ull);
+        CU(cudaMemcpyAsync(ctr.data(), b->ctr_dev, sizeof(unsigned long long) * CTR_PER_LAUNCH * slot, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof(*stats));
         for (auto &ln : launches) {
             const PairClass &B = b->pc[ln.cb], &K = b->pc[ln.ck];
-            const int64_t nq = (int64_t)ctr[3 * ln.slot], npq = (int64_t)ctr[3 * ln.slot + 1];
+            const int64_t nq = (int64_t)(ctr[CTR_PER_LAUNCH * ln.slot] + ctr[CTR_PER_LAUNCH * ln.slot + 3]);
+            const int64_t npq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 1];
+            stats->slow_quartets += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 3];
             const int64_t nfn = (int64_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
-            stats->candidates += (int64_t)ctr[3 * ln.slot + 2];
+            stats->candidates += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 2];
             stats->quartets += nq;
             stats->prim_quartets += npq;
             stats->fn_quartets += nq * nfn;

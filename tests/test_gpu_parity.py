@@ -152,7 +152,7 @@ def test_rhf_mp2_end_to_end_vs_reference(golden, name):
 def test_tight_convergence_is_noise_limited(golden):
     """conver=1e-14 asks RMS(P) to drop below the rounding noise of the Fock build itself: the iteration
     count then depends on summation order (the device reductions use FP64 atomics), so only convergence
-    and the energy are asserted.  The oracle-backed CPU test reproduces the reference's 20 iterations."""
+    and the energy are asserted.  (The oracle-backed CPU driver needs 14 iterations where the reference needs 20.)"""
     a = golden("anchors.json")["h2o_sto3g_incore_tight"]
     mol = Molecule(synth.water(), "sto-3g")
     mol.RHF(doPrint=False, conver=1e-14)
