@@ -308,13 +308,12 @@ template <int L, class RS>
 __device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, double cck, double X, double Y, double Z,
                                        const double *__restrict__ boys_tab)
 {
-    const double pq = pb + pk;
-    const double ipq = 1.0 / pq;
-    const double alpha = pb * pk * ipq;
+    const double rs = rsqrt(pb + pk);     // one reciprocal square root serves 1/(p+q) and 1/sqrt(p+q)
+    const double alpha = pb * pk * (rs * rs);
     const double T = alpha * (X * X + Y * Y + Z * Z);
     double Fs[L + 1];
     boys_eval<L>(T, boys_tab, Fs);
-    double s = ccb * cck * sqrt(ipq);   // 2 pi^2.5 /(p q sqrt(p+q)) * c's * K's
+    double s = ccb * cck * rs;            // 2 pi^2.5 /(p q sqrt(p+q)) * c's * K's
     const double m2a = -2.0 * alpha;
 #pragma unroll
     for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
@@ -355,8 +354,10 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
 #pragma unroll
         for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
 
+        PrimPair k_next = ld_prim(kp + kh.poff);
         for (int ik = 0; ik < kh.pnum; ++ik) {
-            const PrimPair k = ld_prim(kp + kh.poff + ik);
+            const PrimPair k = k_next;
+            if (ik + 1 < kh.pnum) k_next = ld_prim(kp + kh.poff + ik + 1);   // in flight while this one is consumed
             const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
             RStore<L, RSMEM> R;
             if constexpr (RSMEM) {
