@@ -118,10 +118,27 @@ __device__ __forceinline__ PairHdr ld_hdr(const PairHdr *p)
     return r;
 }
 
-// Boys table: rows T0 = i/8, i = 0..320; columns k = 0..8: F_{L+k}(T0)/k!, column 9: exp(-T0).
-constexpr int BOYS_ROWS = 321;
+// Boys table: rows T0 = i/8, i = 0..480; columns k = 0..8: F_{L+k}(T0)/k!, column 9: exp(-T0).
+// Beyond T = 60 exp(-T)/(2T) is below 2e-17 of F_m(T) for every m <= 8, so the large-T branch is the pure
+// asymptotic series (no exp(), no table) — and it is the COMMON branch in extended systems, where most
+// surviving quartets are long-range (T = alpha R^2 >> 60).
+constexpr int BOYS_ROWS = 481;
 constexpr int BOYS_STRIDE = 10;
-constexpr double BOYS_TMAX = 40.0;
+constexpr double BOYS_TMAX = 60.0;
+
+// 1/sqrt(x) to full double precision without the slow-path branches of the library routine:
+// MUFU.RSQ64H seed (2^-22) + two Newton steps.  x is a sum of exponents or a Boys argument >= 60 here.
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
 constexpr int BOYS_MAXL = 8;
 
 // ------------------------------------------------------------------------------------------
@@ -157,14 +174,13 @@ __device__ __forceinline__ void boys_eval(double T, const double *__restrict__ t
             });
         }
     } else {
-        const double it = 1.0 / T;
-        F[0] = 0.88622692545275801365 * sqrt(it);             // sqrt(pi)/2 / sqrt(T)
+        const double rt = fast_rsqrt(T);
+        F[0] = 0.88622692545275801365 * rt;                   // sqrt(pi)/2 / sqrt(T)
         if constexpr (L > 0) {
-            const double e = (T < 120.0) ? exp(-T) : 0.0;
-            const double hit = 0.5 * it;
+            const double hit = 0.5 * (rt * rt);                // 1/(2T)
             sfor<0, L>([&](auto I) {
                 constexpr int m = decltype(I)::value;
-                F[m + 1] = ((2 * m + 1) * F[m] - e) * hit;
+                F[m + 1] = ((2 * m + 1) * hit) * F[m];
             });
         }
     }
@@ -196,13 +212,10 @@ __device__ __forceinline__ void boys_eval_rt(int L, double T, const double *__re
             for (int m = L; m > 0; --m) F[m - 1] = fma(t2, F[m], e) / (double)(2 * m - 1);
         }
     } else {
-        const double it = 1.0 / T;
-        F[0] = 0.88622692545275801365 * sqrt(it);
-        if (L > 0) {
-            const double e = (T < 120.0) ? exp(-T) : 0.0;
-            const double hit = 0.5 * it;
-            for (int m = 0; m < L; ++m) F[m + 1] = ((2 * m + 1) * F[m] - e) * hit;
-        }
+        const double rt = fast_rsqrt(T);
+        F[0] = 0.88622692545275801365 * rt;
+        const double hit = 0.5 * (rt * rt);
+        for (int m = 0; m < L; ++m) F[m + 1] = ((2 * m + 1) * hit) * F[m];
     }
 }
 
@@ -308,7 +321,7 @@ template <int L, class RS>
 __device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, double cck, double X, double Y, double Z,
                                        const double *__restrict__ boys_tab)
 {
-    const double rs = rsqrt(pb + pk);     // one reciprocal square root serves 1/(p+q) and 1/sqrt(p+q)
+    const double rs = fast_rsqrt(pb + pk);   // one reciprocal square root serves 1/(p+q) and 1/sqrt(p+q)
     const double alpha = pb * pk * (rs * rs);
     const double T = alpha * (X * X + Y * Y + Z * Z);
     double Fs[L + 1];
@@ -334,7 +347,7 @@ __device__ __noinline__ void prim_R_smem(double *base, int stride, double pb, do
 // One contracted shell quartet, ket component pairs [CD0, CD0+NCDC), class-specialised.
 // out[ab*NCDC + cdi] accumulates (ab|cd) WITHOUT the per-component normalisation.
 // ------------------------------------------------------------------------------------------
-template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM>
+template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SERIAL_CHUNKS>
 __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const PrimPair *__restrict__ bp,
                                                    const PairHdr &kh, const PrimPair *__restrict__ kp,
                                                    const double *__restrict__ boys_tab, double *r_smem, int r_stride,
@@ -365,7 +378,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
                 R.stride = r_stride;
                 // a quartet with ONE primitive quartet keeps its R table in shared memory across the
                 // ket-component chunks: only the first chunk builds it
-                if (CD0 == 0 || bh.pnum * kh.pnum != 1)
+                if (!SERIAL_CHUNKS || CD0 == 0 || bh.pnum * kh.pnum != 1)
                     prim_R_smem<L>(r_smem, r_stride, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
             } else {
                 prim_R<L>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);

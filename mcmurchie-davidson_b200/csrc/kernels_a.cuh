@@ -3,6 +3,8 @@
 // integrals live in registers.  When the (ab|cd) block is too large for the register file the ket
 // component pairs are processed in NCHUNK static chunks (R is rebuilt per chunk).
 #pragma once
+#include <algorithm>
+
 #include "core.cuh"
 
 namespace mmdb {
@@ -40,6 +42,13 @@ __host__ __device__ constexpr int chunk_ncd()
             if (NCD % c == 0 && NAB * c <= 36 && NHB * c <= 40) best = c;
     }
     return best;
+}
+
+// chunk = CTA property (true) or serial loop inside the thread (false)
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr bool block_chunks()
+{
+    return ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() >= 2;
 }
 
 template <int LA, int LB, int LC, int LD>
@@ -239,7 +248,7 @@ static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, cons
     }
 }
 
-template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC>
+template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC, bool SERIAL_CHUNKS>
 __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, bool valid, const PairHdr &bh,
                                           const PairHdr &kh, const double *boys_tab, bool samePair, bool ket_uniform)
 {
@@ -247,7 +256,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     constexpr int NAB = NA * NB, NCD = NC * ND;
     double out[NAB * NCDC];
     if (valid)
-        eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>()>(
+        eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS>(
             bh, a.braP, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + BOYS_ROWS * BOYS_STRIDE + threadIdx.x,
             KA_THREADS, out);
     if constexpr (EPI == EPI_STORE) {
@@ -290,34 +299,57 @@ __global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
     for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = a.boys_tab[x];
     __syncthreads();
     const unsigned long long n = a.count_dev ? *a.count_dev : a.n;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     // Block-uniform trip count: every warp stays in the loop (the digestion uses warp shuffles) and, for the
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
     // barrier per quartet so they stream through the code together (one fetch serves all of them).
     constexpr bool LOCKSTEP = (LA + LB + LC + LD >= 3);
-    // the list entry of the NEXT quartet is read one iteration ahead
-    unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x;
+    // Chunked classes: the ket-component chunk is a property of the CTA (blockIdx.x % NCHUNK), not a serial
+    // loop inside the thread.  Each CTA then executes the code of ONE chunk for many quartets, so its
+    // instruction working set is 1/NCHUNK of the kernel and stays cache-resident (ncu: stall_no_instruction
+    // was the top stall with the serial chunk loop); the price is one R build per chunk.
+    constexpr bool BLOCK_CHUNKS = block_chunks<LA, LB, LC, LD>();
+    const int my_chunk = BLOCK_CHUNKS ? (int)(blockIdx.x % NCHUNK) : 0;
+    const unsigned long long worker = BLOCK_CHUNKS ? blockIdx.x / NCHUNK : blockIdx.x;
+    const unsigned long long nworkers = BLOCK_CHUNKS ? gridDim.x / NCHUNK : gridDim.x;
+    const unsigned long long wstride = nworkers * blockDim.x;
     const long long lstep = a.list_step;
-    uint2 ij_next = make_uint2(0u, 0u);
-    if (base < n) ij_next = __ldg(a.list + (long long)min(base + threadIdx.x, n - 1) * lstep);
-    for (; base < n; base += stride) {
-        if constexpr (LOCKSTEP) __syncthreads();
-        const unsigned long long e = base + threadIdx.x;
-        const bool valid = e < n;
-        const uint2 ij = ij_next;
-        const PairHdr bh = ld_hdr(a.braH + ij.x);
-        const PairHdr kh = ld_hdr(a.ketH + ij.y);
-        if (base + stride < n) ij_next = __ldg(a.list + (long long)min(e + stride, n - 1) * lstep);
-        const bool samePair = a.same_class && (ij.x == ij.y);
-        bool ket_uniform = false;
-        if constexpr (EPI == EPI_DIGEST) {
-            const unsigned y0 = __shfl_sync(0xffffffffu, ij.y, 0);
-            ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid);
+    auto run_list = [&](auto CHSEL) {
+        constexpr int chsel = decltype(CHSEL)::value;     // -1: all chunks serially inside the thread
+        // the list entry of the NEXT quartet is read one iteration ahead
+        unsigned long long base = worker * blockDim.x;
+        uint2 ij_next = make_uint2(0u, 0u);
+        if (base < n) ij_next = __ldg(a.list + (long long)min(base + threadIdx.x, n - 1) * lstep);
+        for (; base < n; base += wstride) {
+            if constexpr (LOCKSTEP) __syncthreads();
+            const unsigned long long e = base + threadIdx.x;
+            const bool valid = e < n;
+            const uint2 ij = ij_next;
+            const PairHdr bh = ld_hdr(a.braH + ij.x);
+            const PairHdr kh = ld_hdr(a.ketH + ij.y);
+            if (base + wstride < n) ij_next = __ldg(a.list + (long long)min(e + wstride, n - 1) * lstep);
+            const bool samePair = a.same_class && (ij.x == ij.y);
+            bool ket_uniform = false;
+            if constexpr (EPI == EPI_DIGEST) {
+                const unsigned y0 = __shfl_sync(0xffffffffu, ij.y, 0);
+                ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid);
+            }
+            if constexpr (chsel >= 0) {
+                run_chunk<LA, LB, LC, LD, EPI, chsel * NCDC, NCDC, false>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform);
+            } else {
+                sfor<0, NCHUNK>([&](auto CH) {
+                    constexpr int ch = decltype(CH)::value;
+                    run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC, true>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform);
+                });
+            }
         }
+    };
+    if constexpr (BLOCK_CHUNKS) {
+        if (worker >= nworkers) return;      // grid not a multiple of NCHUNK: surplus CTAs have no chunk
         sfor<0, NCHUNK>([&](auto CH) {
-            constexpr int ch = decltype(CH)::value;
-            run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform);
+            if (my_chunk == decltype(CH)::value) run_list(CH);
         });
+    } else {
+        run_list(std::integral_constant<int, -1>{});
     }
 }
 
@@ -343,12 +375,14 @@ cudaError_t launch_class_impl(const EriArgs &a, int epi, int grid, cudaStream_t 
         for (int &o : occ)
             if (o < 1) o = 1;
     }
+    constexpr int NCH = block_chunks<LA, LB, LC, LD>() ? ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() : 1;
+    auto shape = [&](int o) { return std::max(NCH, (grid * o) / NCH * NCH); };   // multiple of the chunk count
     if (epi == EPI_STORE)
-        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<grid * occ[0], KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<shape(occ[0]), KA_THREADS, smem, st>>>(a);
     else if (epi == EPI_DIGEST)
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<grid * occ[1], KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<shape(occ[1]), KA_THREADS, smem, st>>>(a);
     else
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW><<<grid * occ[2], KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW><<<shape(occ[2]), KA_THREADS, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -115,14 +115,14 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
             for (int x = 0; x < nhb; ++x) G[x] = 0.0;
             for (int ik = 0; ik < kh.pnum; ++ik) {
                 const PrimPair k = ld_prim(a.ketP + kh.poff + ik);
-                const double pq = b.p + k.p, ipq = 1.0 / pq;
-                const double alpha = b.p * k.p * ipq;
+                const double rs = fast_rsqrt(b.p + k.p);
+                const double alpha = b.p * k.p * (rs * rs);
                 const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
                 const double T = alpha * (X * X + Y * Y + Z * Z);
                 double Fs[KB_MAXL + 1];
                 boys_eval_rt(L, T, s_boys, Fs);
                 {
-                    double s = b.cc * k.cc * sqrt(ipq);
+                    double s = b.cc * k.cc * rs;
                     const double m2a = -2.0 * alpha;
                     for (int nn = 0; nn <= L; ++nn) { Fs[nn] *= s; s *= m2a; }
                 }

@@ -21,7 +21,7 @@ E_TOL = 1e-9
 
 def test_boys_device_vs_oracle(oracle):
     rng = np.random.default_rng(0)
-    Ts = np.concatenate([10 ** rng.uniform(-9, 6, 3000), rng.uniform(0, 45, 3000), [0.0, 39.999999, 40.0, 40.000001, 119.9, 120.1]])
+    Ts = np.concatenate([10 ** rng.uniform(-9, 6, 3000), rng.uniform(0, 45, 3000), [0.0, 39.999999, 40.0, 40.000001, 59.9999, 60.0, 60.0001, 119.9, 120.1]])
     for n in (0, 2, 5, 8):
         got = E.boys(n, Ts)
         ref = np.array([[oracle.boys(m, T) for m in range(n + 1)] for T in Ts])
