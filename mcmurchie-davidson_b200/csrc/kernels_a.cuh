@@ -229,6 +229,73 @@ __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestG
     }
 }
 
+// Out-of-line variant of digest_block for the classes whose chunks hold ONE ket component pair (every class
+// with a d shell in the ket or L >= 4 with a dp/dd bra): the (c,d) components are run-time arguments, so the
+// digestion code is emitted once per kernel instead of once per chunk.  With up to 18 chunks per class the
+// unrolled digestion was the bulk of the instruction footprint (ncu: stall_no_instruction dominant).
+template <int LA, int LB, int LC, int LD>
+__device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB, int bfC, int bfD, int c, int d, double scd,
+                                          bool active, bool ket_uniform, const double *__restrict__ out)
+{
+    constexpr int NA = ncart(LA), NB = ncart(LB);
+    const DigestGeom g = make_geom(dg.N, bfA, bfB, bfC, bfD);
+    const double *__restrict__ P = dg.dPre;
+    const double *__restrict__ SQ = dg.SQ;
+    double *__restrict__ G = dg.Gre;
+    const long long ocd = g.cd.base + c * g.cd.s0 + d * g.cd.s1;
+    double jcd = 0.0;
+    if (active) {
+        const double tol = dg.tol;
+        const double pcd = __ldg(&P[ocd]), qcd = __ldg(&SQ[ocd]);
+        const double pcd4 = 4.0 * fabs(pcd);
+        double Pbc[NB], Pbd[NB], Kbc[NB], Kbd[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            Pbc[b] = __ldg(&P[g.pbc.base + b * g.pbc.s0 + c * g.pbc.s1]);
+            Pbd[b] = __ldg(&P[g.pbd.base + b * g.pbd.s0 + d * g.pbd.s1]);
+            Kbc[b] = 0.0;
+            Kbd[b] = 0.0;
+        }
+        sfor<0, NA>([&](auto A_) {
+            constexpr int a = decltype(A_)::value;
+            const double pac = __ldg(&P[g.pac.base + a * g.pac.s0 + c * g.pac.s1]);
+            const double pad = __ldg(&P[g.pad.base + a * g.pad.s0 + d * g.pad.s1]);
+            double kac = 0.0, kad = 0.0;
+            sfor<0, NB>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                constexpr double s8 = 8.0 * comp_scale(LA, a) * comp_scale(LB, b);
+                const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
+                const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
+                double dmax = fmax(4.0 * fabs(pab), pcd4);
+                dmax = fmax(dmax, fmax(fmax(fabs(pac), fabs(pad)), fmax(fabs(Pbc[b]), fabs(Pbd[b]))));
+                const double bound = (qab * qcd) * dmax;
+                const double e = (bound < tol) ? 0.0 : (s8 * scd) * out[a * NB + b];
+                const double eq = -0.25 * e;
+                red_add_f64(&G[oab], pcd * e);
+                jcd = fma(pab, e, jcd);
+                kac = fma(Pbd[b], eq, kac);
+                Kbd[b] = fma(pac, eq, Kbd[b]);
+                kad = fma(Pbc[b], eq, kad);
+                Kbc[b] = fma(pad, eq, Kbc[b]);
+            });
+            red_add_f64(&G[g.gac.base + a * g.gac.s0 + c * g.gac.s1], kac);
+            red_add_f64(&G[g.gad.base + a * g.gad.s0 + d * g.gad.s1], kad);
+        });
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            red_add_f64(&G[g.gbc.base + b * g.gbc.s0 + c * g.gbc.s1], Kbc[b]);
+            red_add_f64(&G[g.gbd.base + b * g.gbd.s0 + d * g.gbd.s1], Kbd[b]);
+        }
+    }
+    if (ket_uniform) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) jcd += __shfl_xor_sync(0xffffffffu, jcd, o);
+        if ((threadIdx.x & 31) == 0) red_add_f64(&G[ocd], jcd);
+    } else if (active) {
+        red_add_f64(&G[ocd], jcd);
+    }
+}
+
 static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, const PairHdr &bh, const PairHdr &kh, bool samePair,
                                                int la, int lb, int lc, int ld, int cd0, int ncdc, const double *vals)
 {
@@ -276,8 +343,20 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     } else if constexpr (EPI == EPI_DIGEST) {
         // block addresses are rebuilt here (a few integer ops) so they are not live across the ERI evaluation;
         // the warp-level J_cd reduction inside runs for every lane (inactive lanes contribute zeros)
-        const DigestGeom geom = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
-        digest_block<LA, LB, LC, LD, CD0, NCDC>(a.dg, geom, valid, ket_uniform, out);
+        if constexpr (NCD > 1 && (NCDC == 1 || r_in_smem<LA, LB, LC, LD>())) {
+            sfor<0, NCDC>([&](auto CDI) {
+                constexpr int cdi = decltype(CDI)::value;
+                constexpr int cd = CD0 + cdi;
+                double tmp[NAB];
+#pragma unroll
+                for (int x = 0; x < NAB; ++x) tmp[x] = out[x * NCDC + cdi];
+                digest_cd_rt<LA, LB, LC, LD>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, cd / ND, cd % ND,
+                                             comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND), valid, ket_uniform, tmp);
+            });
+        } else {
+            const DigestGeom geom = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
+            digest_block<LA, LB, LC, LD, CD0, NCDC>(a.dg, geom, valid, ket_uniform, out);
+        }
     } else {
         // second list (diagonal-type quartets, complex densities): per-function digestion, out of line
         if (valid) {
