@@ -351,7 +351,7 @@ template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SE
 __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const PrimPair *__restrict__ bp,
                                                    const PairHdr &kh, const PrimPair *__restrict__ kp,
                                                    const double *__restrict__ boys_tab, double *r_smem, int r_stride,
-                                                   double (&out)[ncart(LA) * ncart(LB) * NCDC])
+                                                   int ib0, int ib1, double (&out)[ncart(LA) * ncart(LB) * NCDC])
 {
     constexpr int LBRA = LA + LB, LKET = LC + LD, L = LBRA + LKET;
     constexpr int NA = ncart(LA), NB = ncart(LB), ND = ncart(LD);
@@ -361,7 +361,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
 #pragma unroll
     for (int x = 0; x < NAB * NCDC; ++x) out[x] = 0.0;
 
-    for (int ib = 0; ib < bh.pnum; ++ib) {
+    for (int ib = ib0; ib < ib1; ++ib) {       // [ib0,ib1): this entry's slice of the bra primitive pairs
         const PrimPair b = ld_prim(bp + bh.poff + ib);
         double G[NHB * NCDC];
 #pragma unroll
@@ -378,7 +378,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
                 R.stride = r_stride;
                 // a quartet with ONE primitive quartet keeps its R table in shared memory across the
                 // ket-component chunks: only the first chunk builds it
-                if (!SERIAL_CHUNKS || CD0 == 0 || bh.pnum * kh.pnum != 1)
+                if (!SERIAL_CHUNKS || CD0 == 0 || (ib1 - ib0) * kh.pnum != 1)
                     prim_R_smem<L>(r_smem, r_stride, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
             } else {
                 prim_R<L>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
@@ -530,5 +530,13 @@ struct EriArgs {
 // EPI_DIGEST: every entry satisfies the block-digestion preconditions (the screening kernel sorts the
 // others into a second list); EPI_DIGEST_SLOW: per-function digestion for that second list
 enum { EPI_STORE = 0, EPI_DIGEST = 1, EPI_DIGEST_SLOW = 2 };
+
+// Direct-build list entries carry a slice id in the top byte of the bra pair index: slice s covers the bra
+// primitive pairs [s*BRA_SLICE, (s+1)*BRA_SLICE).  Deeply contracted quartets ((s8 s8|s8 s8) = 4096 primitive
+// quartets) are thereby spread over up to 8 threads; J/K digestion is linear in the integrals, so every slice
+// digests its own partial block.  Bounds the longest serial thread (the tail of every launch).
+constexpr int BRA_SLICE = 8;
+constexpr unsigned SLICE_SHIFT = 24;
+constexpr unsigned PAIR_MASK = (1u << SLICE_SHIFT) - 1u;
 
 }  // namespace mmdb

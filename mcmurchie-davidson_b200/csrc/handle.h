@@ -35,6 +35,7 @@ struct PairClass {
     int la = 0, lb = 0;
     int npairs = 0;
     int64_t nprimpairs = 0;
+    size_t slice_entries = 0;   // sum over pairs of ceil(pnum / BRA_SLICE): list entries one ket row can produce
     std::vector<mmdb::PairHdr> hdr;
     std::vector<mmdb::PrimPair> prim;
     mmdb::PairHdr *hdr_dev = nullptr;

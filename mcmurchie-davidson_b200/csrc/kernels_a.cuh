@@ -317,7 +317,8 @@ static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, cons
 
 template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC, bool SERIAL_CHUNKS>
 __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, bool valid, const PairHdr &bh,
-                                          const PairHdr &kh, const double *boys_tab, bool samePair, bool ket_uniform)
+                                          const PairHdr &kh, const double *boys_tab, bool samePair, bool ket_uniform,
+                                          int ib0, int ib1)
 {
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND;
@@ -325,7 +326,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     if (valid)
         eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS>(
             bh, a.braP, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + BOYS_ROWS * BOYS_STRIDE + threadIdx.x,
-            KA_THREADS, out);
+            KA_THREADS, ib0, ib1, out);
     if constexpr (EPI == EPI_STORE) {
         if (valid) {
             double *o = a.out + e * (unsigned long long)(NAB * NCD);
@@ -402,22 +403,26 @@ __global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
             if constexpr (LOCKSTEP) __syncthreads();
             const unsigned long long e = base + threadIdx.x;
             const bool valid = e < n;
-            const uint2 ij = ij_next;
+            uint2 ij = ij_next;
+            const int slice = (EPI == EPI_STORE) ? 0 : (int)(ij.x >> SLICE_SHIFT);
+            if constexpr (EPI != EPI_STORE) ij.x &= PAIR_MASK;
             const PairHdr bh = ld_hdr(a.braH + ij.x);
             const PairHdr kh = ld_hdr(a.ketH + ij.y);
             if (base + wstride < n) ij_next = __ldg(a.list + (long long)min(e + wstride, n - 1) * lstep);
             const bool samePair = a.same_class && (ij.x == ij.y);
+            const int ib0 = (EPI == EPI_STORE) ? 0 : slice * BRA_SLICE;
+            const int ib1 = (EPI == EPI_STORE) ? bh.pnum : min(bh.pnum, ib0 + BRA_SLICE);
             bool ket_uniform = false;
             if constexpr (EPI == EPI_DIGEST) {
                 const unsigned y0 = __shfl_sync(0xffffffffu, ij.y, 0);
                 ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid);
             }
             if constexpr (chsel >= 0) {
-                run_chunk<LA, LB, LC, LD, EPI, chsel * NCDC, NCDC, false>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform);
+                run_chunk<LA, LB, LC, LD, EPI, chsel * NCDC, NCDC, false>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
             } else {
                 sfor<0, NCHUNK>([&](auto CH) {
                     constexpr int ch = decltype(CH)::value;
-                    run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC, true>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform);
+                    run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC, true>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
                 });
             }
         }

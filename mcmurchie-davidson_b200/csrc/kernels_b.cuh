@@ -97,12 +97,16 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
         const int c = cd / ND, d = cd % ND;
         const int cx = cart_pow_rt(lc, c, 0), cy = cart_pow_rt(lc, c, 1), cz = cart_pow_rt(lc, c, 2);
         const int dx = cart_pow_rt(ld, d, 0), dy = cart_pow_rt(ld, d, 1), dz = cart_pow_rt(ld, d, 2);
-        const uint2 ij = __ldg(a.list + (long long)e * a.list_step);
+        uint2 ij = __ldg(a.list + (long long)e * a.list_step);
+        const int slice = (EPI == EPI_STORE) ? 0 : (int)(ij.x >> SLICE_SHIFT);
+        if (EPI != EPI_STORE) ij.x &= PAIR_MASK;
         const PairHdr bh = ld_hdr(a.braH + ij.x);
         const PairHdr kh = ld_hdr(a.ketH + ij.y);
         double out[36];
         for (int x = 0; x < NAB; ++x) out[x] = 0.0;
-        for (int ib = 0; ib < bh.pnum; ++ib) {
+        const int ib0 = (EPI == EPI_STORE) ? 0 : slice * BRA_SLICE;
+        const int ib1 = (EPI == EPI_STORE) ? bh.pnum : min(bh.pnum, ib0 + BRA_SLICE);
+        for (int ib = ib0; ib < ib1; ++ib) {
             const PrimPair b = ld_prim(a.braP + bh.poff + ib);
             ETabRT Eb;
             {

@@ -219,7 +219,10 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
             P.hdr.push_back(t.h);
         }
         P.nprimpairs = (int64_t)P.prim.size();
+        P.slice_entries = 0;
+        for (auto &h : P.hdr) P.slice_entries += (size_t)((h.pnum + BRA_SLICE - 1) / BRA_SLICE);
         if (P.npairs == 0) continue;
+        if ((unsigned)P.npairs > PAIR_MASK) return fail(MMDB_ERR_UNSUPPORTED, "more than 2^24 shell pairs in one class");
         std::vector<int> K(P.npairs);
         std::vector<int2> shs(P.npairs);
         for (int i = 0; i < P.npairs; ++i) {
@@ -417,6 +420,7 @@ struct ScreenArgs {
     const int *bf0;                // first function index per shell
     long long cap;                 // list capacity (the slow list starts at list[cap-1] and grows downwards)
     unsigned long long *count_slow;
+    unsigned long long *nquart;    // shell quartets (list entries count bra-primitive slices)
     const double *DS;
     const unsigned long long *dglob;
     double tol;
@@ -449,13 +453,15 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const int2 cd = s.sh_ket[j];
         const unsigned long long kj = (unsigned long long)s.K_ket[j];
         const int cbase = c0 + threadIdx.x * SCR_CPT;
-        unsigned bits = 0, sbits = 0, ncand = 0;
+        unsigned bits = 0, sbits = 0, ncand = 0, nent_fast = 0, nent_slow = 0;
+        unsigned nsl[SCR_CPT];
         unsigned long long kk = 0;
         const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
         const bool ketDiag = cd.x == cd.y;
 #pragma unroll
         for (int k = 0; k < SCR_CPT; ++k) {
             const int i = cbase + k;
+            nsl[k] = 0;
             bool pass = (i < s.nbra) && (i >= cstart);
             if (pass) {
                 ++ncand;
@@ -475,18 +481,20 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                 }
                 if (pass) {
                     bits |= 1u << k;
-                    kk += (unsigned long long)s.K_bra[i] * kj;
-                    if (s.split) {
-                        // block digestion needs A != B, C != D and different leading shells (kernels_a.cuh)
-                        const bool slow = s.force_slow || ketDiag || ab.x == ab.y || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
-                        if (slow) sbits |= 1u << k;
-                    }
+                    const int kb = s.K_bra[i];
+                    kk += (unsigned long long)kb * kj;
+                    // one list entry per slice of BRA_SLICE bra primitive pairs (direct builds only)
+                    nsl[k] = s.split ? (unsigned)((kb + BRA_SLICE - 1) / BRA_SLICE) : 1u;
+                    bool slow = false;
+                    if (s.split)   // block digestion needs A != B, C != D and different leading shells (kernels_a.cuh)
+                        slow = s.force_slow || ketDiag || ab.x == ab.y || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
+                    if (slow) { sbits |= 1u << k; nent_slow += nsl[k]; }
+                    else nent_fast += nsl[k];
                 }
             }
         }
         // block-wide exclusive scan of the survivor counts (fast list in the low half, slow list in the high half)
-        const unsigned nslow = __popc(sbits), cnt = __popc(bits) - nslow;
-        unsigned long long incl = (unsigned long long)cnt | ((unsigned long long)nslow << 32);
+        unsigned long long incl = (unsigned long long)nent_fast | ((unsigned long long)nent_slow << 32);
         const unsigned long long mine = incl;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -494,7 +502,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
             if (lane >= o) incl += v;
         }
         unsigned long long ks = kk;
-        unsigned cs = ncand;
+        unsigned cs = ncand | ((unsigned)__popc(bits) << 16);      // candidates | shell quartets (<= 8 each per thread)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             ks += __shfl_xor_sync(0xffffffffu, ks, o);
@@ -505,14 +513,16 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long tot = 0, tk = 0;
-            unsigned tc = 0;
+            unsigned tc = 0, tq = 0;
             for (int w = 0; w < SCR_THREADS / 32; ++w) {
                 const unsigned long long c = s_wcnt[w];
                 s_wcnt[w] = tot;
                 tot += c;
                 tk += s_wk[w];
-                tc += s_wcand[w];
+                tc += s_wcand[w] & 0xffffu;
+                tq += s_wcand[w] >> 16;
             }
+            if (tq) atomicAdd(s.nquart, (unsigned long long)tq);
             const unsigned tf = (unsigned)(tot & 0xffffffffull), tsl = (unsigned)(tot >> 32);
             s_base = tf ? atomicAdd(s.count, (unsigned long long)tf) : 0ull;
             s_base_slow = tsl ? atomicAdd(s.count_slow, (unsigned long long)tsl) : 0ull;
@@ -527,9 +537,11 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
 #pragma unroll
             for (int k = 0; k < SCR_CPT; ++k)
                 if (bits & (1u << k)) {
-                    const uint2 ent = make_uint2((unsigned)(cbase + k), (unsigned)j);
-                    if (sbits & (1u << k)) s.list[spos--] = ent;
-                    else s.list[pos++] = ent;
+                    for (unsigned sl = 0; sl < nsl[k]; ++sl) {
+                        const uint2 ent = make_uint2((unsigned)(cbase + k) | (sl << SLICE_SHIFT), (unsigned)j);
+                        if (sbits & (1u << k)) s.list[spos--] = ent;
+                        else s.list[pos++] = ent;
+                    }
                 }
         }
         __syncthreads();
@@ -629,7 +641,7 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
     return MMDB_OK;
 }
 
-constexpr int CTR_PER_LAUNCH = 4;   // survivors (fast list), primitive quartets, candidates, survivors (slow list)
+constexpr int CTR_PER_LAUNCH = 5;   // entries (fast list), primitive quartets, candidates, entries (slow list), shell quartets
 
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
                       bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, cudaStream_t st)
@@ -640,7 +652,7 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
     s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
     s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
     s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = b->list_dev;
-    s.count = b->ctr_dev + CTR_PER_LAUNCH * slot; s.primq = s.count + 1; s.cand = s.count + 2; s.count_slow = s.count + 3;
+    s.count = b->ctr_dev + CTR_PER_LAUNCH * slot; s.primq = s.count + 1; s.cand = s.count + 2; s.count_slow = s.count + 3; s.nquart = s.count + 4;
     s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
     const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(row1 - row0) * ntile;
@@ -719,10 +731,11 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         for (int ck = 0; ck <= cb; ++ck) {
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
-            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.npairs);
+            // rows of this shard only count towards the list capacity
+            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.slice_entries * (size_t)nshards);
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                const size_t cap = (size_t)(row1 - row0) * B.npairs;
+                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.slice_entries;   // room for every bra-primitive slice
                 CHK(ensure_list(b, cap));
                 if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
                 Launch ln{cb, ck, slot, nullptr, nullptr, nullptr};
@@ -757,7 +770,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         std::memset(stats, 0, sizeof(*stats));
         for (auto &ln : launches) {
             const PairClass &B = b->pc[ln.cb], &K = b->pc[ln.ck];
-            const int64_t nq = (int64_t)(ctr[CTR_PER_LAUNCH * ln.slot] + ctr[CTR_PER_LAUNCH * ln.slot + 3]);
+            const int64_t nq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 4];
             const int64_t npq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 1];
             stats->slow_quartets += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 3];
             const int64_t nfn = (int64_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
