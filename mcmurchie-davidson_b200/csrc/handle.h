@@ -63,6 +63,8 @@ struct mmdb_basis {
     size_t list_cap = 0;
     unsigned long long *ctr_dev = nullptr;        // counters
     int nctr = 0;
+    cudaStream_t aux_stream = nullptr;            // small class pairs run here, concurrently with the big ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double *scratch_dev = nullptr;
     size_t scratch_cap = 0;   // doubles
 };

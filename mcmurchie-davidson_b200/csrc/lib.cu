@@ -120,6 +120,7 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
     cudaFree(b->Dabs_dev); cudaFree(b->DS_dev); cudaFree(b->dglob_dev); cudaFree(b->list_dev);
     cudaFree(b->ctr_dev); cudaFree(b->scratch_dev);
+    if (b->aux_stream) { cudaStreamDestroy(b->aux_stream); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
     delete b;
     return MMDB_OK;
 }
@@ -644,14 +645,15 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
 constexpr int CTR_PER_LAUNCH = 5;   // entries (fast list), primitive quartets, candidates, entries (slow list), shell quartets
 
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
-                      bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, cudaStream_t st)
+                      bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, uint2 *list,
+                      cudaStream_t st)
 {
     ScreenArgs s;
     s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
     s.K_bra = B.K_dev; s.K_ket = K.K_dev;
     s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
     s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
-    s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = b->list_dev;
+    s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = list;
     s.count = b->ctr_dev + CTR_PER_LAUNCH * slot; s.primq = s.count + 1; s.cand = s.count + 2; s.count_slow = s.count + 3; s.nquart = s.count + 4;
     s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
     const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
@@ -665,6 +667,7 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
 
 static const size_t LIST_CAP = (size_t)1 << 27;      // entries per screening chunk (1 GiB of uint2)
 static const size_t SCRATCH_CAP = (size_t)1 << 27;   // doubles (1 GiB)
+static const size_t AUX_MAX_CANDIDATES = (size_t)6 << 20;   // class pairs up to this many candidates per shard go to the aux stream
 
 extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
 {
@@ -687,7 +690,7 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
                 CHK(ensure_list(b, cap));
                 CHK(ensure_scratch(b, cap * nfn));
                 if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
-                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, st));
+                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, b->list_dev, st));
                 EriArgs a;
                 std::memset(&a, 0, sizeof(a));
                 a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
@@ -726,43 +729,77 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     struct Launch { int cb, ck, slot; cudaEvent_t e0, em, e1; };
     std::vector<Launch> launches;
     const bool timing = (flags & 1) != 0;
-    int slot = 0;
+    // Two queues.  Class pairs with few candidates (the d-heavy classes: a few thousand to a few million
+    // quartets) cannot fill 148 SMs and are bounded by the latency of their longest thread; they run on an
+    // auxiliary stream with their own list buffer, concurrently with the big classes on the caller's stream.
+    // With per-class event timing everything stays on one stream.
+    struct Task { int cb, ck, row0, row1; size_t cap; bool aux; };
+    std::vector<Task> tasks;
+    size_t cap_main = 0, cap_aux = 0;
     for (int cb = 0; cb < MMDB_NCLASS_PAIR; ++cb)
         for (int ck = 0; ck <= cb; ++ck) {
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
             // rows of this shard only count towards the list capacity
             size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.slice_entries * (size_t)nshards);
+            const bool small = !timing && (size_t)B.npairs * K.npairs / nshards <= AUX_MAX_CANDIDATES;
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.slice_entries;   // room for every bra-primitive slice
-                CHK(ensure_list(b, cap));
-                if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
-                Launch ln{cb, ck, slot, nullptr, nullptr, nullptr};
-                if (timing) {
-                    CU(cudaEventCreate(&ln.e0));
-                    CU(cudaEventCreate(&ln.em));
-                    CU(cudaEventCreate(&ln.e1));
-                    CU(cudaEventRecord(ln.e0, st));
-                }
-                CHK(run_screen(b, B, K, cb == ck, row0, row1, shard, nshards, false, tol, slot, true, dP_im_dev != nullptr,
-                               (long long)cap, st));
-                if (timing) CU(cudaEventRecord(ln.em, st));
-                EriArgs a;
-                std::memset(&a, 0, sizeof(a));
-                a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
-                a.list = b->list_dev; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.same_class = (cb == ck);
-                a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
-                a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
-                // block-digestible quartets, then the second list (diagonal-type quartets / complex density)
-                CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST, 0, st));
-                a.list = b->list_dev + (cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + 3;
-                CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST_SLOW, 0, st));
-                if (timing) CU(cudaEventRecord(ln.e1, st));
-                launches.push_back(ln);
-                ++slot;
+                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.slice_entries;   // room for every slice
+                tasks.push_back(Task{cb, ck, row0, row1, cap, small});
+                (small ? cap_aux : cap_main) = std::max(small ? cap_aux : cap_main, cap);
             }
         }
+    CHK(ensure_list(b, cap_main + cap_aux));          // [main | aux] regions of one buffer
+    uint2 *list_main = b->list_dev, *list_aux = b->list_dev + cap_main;
+    if ((int)tasks.size() * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
+    cudaStream_t sa = st;
+    if (cap_aux > 0) {
+        if (!b->aux_stream) {
+            CU(cudaStreamCreateWithFlags(&b->aux_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+        }
+        sa = b->aux_stream;
+        CU(cudaEventRecord(b->ev_fork, st));           // density screens + zeroed counters are ready
+        CU(cudaStreamWaitEvent(sa, b->ev_fork, 0));
+    }
+    int slot = 0;
+    // aux tasks first: they are enqueued (and start) while the host is still launching the big classes
+    for (int pass = 0; pass < 2; ++pass)
+        for (const Task &t : tasks) {
+            if (t.aux != (pass == 0)) continue;
+            PairClass &B = b->pc[t.cb], &K = b->pc[t.ck];
+            cudaStream_t s1 = t.aux ? sa : st;
+            uint2 *list = t.aux ? list_aux : list_main;
+            Launch ln{t.cb, t.ck, slot, nullptr, nullptr, nullptr};
+            if (timing) {
+                CU(cudaEventCreate(&ln.e0));
+                CU(cudaEventCreate(&ln.em));
+                CU(cudaEventCreate(&ln.e1));
+                CU(cudaEventRecord(ln.e0, s1));
+            }
+            CHK(run_screen(b, B, K, t.cb == t.ck, t.row0, t.row1, shard, nshards, false, tol, slot, true, dP_im_dev != nullptr,
+                           (long long)t.cap, list, s1));
+            if (timing) CU(cudaEventRecord(ln.em, s1));
+            EriArgs a;
+            std::memset(&a, 0, sizeof(a));
+            a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+            a.list = list; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.same_class = (t.cb == t.ck);
+            a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
+            a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
+            // block-digestible quartets, then the second list (diagonal-type quartets / complex density)
+            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST, 0, s1));
+            a.list = list + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + 3;
+            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST_SLOW, 0, s1));
+            if (timing) CU(cudaEventRecord(ln.e1, s1));
+            launches.push_back(ln);
+            ++slot;
+        }
+    if (cap_aux > 0) {
+        CU(cudaEventRecord(b->ev_join, sa));
+        CU(cudaStreamWaitEvent(st, b->ev_join, 0));    // everything enqueued after this call sees the full G
+    }
     if (stats) {
         std::vector<unsigned long long> ctr(CTR_PER_LAUNCH * (size_t)slot + CTR_PER_LAUNCH, 0ull);
         CU(cudaMemcpyAsync(ctr.data(), b->ctr_dev, sizeof(unsigned long long) * CTR_PER_LAUNCH * slot, cudaMemcpyDeviceToHost, st));
