@@ -2,11 +2,9 @@
 //
 // Replaces mmd/scf.py:97-98 of the reference:
 //     J = einsum('pqrs,sr->pq', TwoE.astype(complex), P);  K = einsum('psqr,sr->pq', TwoE.astype(complex), P)
-// which makes two passes over a 16*N^4-byte complex copy.  Here each CTA streams slabs
-// M[q][r] = TwoE[p][x][q][r] (N*N contiguous doubles) exactly once and produces
-//     J[p][x]  = sum_{q,r} M[q][r] * P[r][q]
-//     K[p][q] += sum_r     M[q][r] * P[x][r]            (for all q)
-// Re and Im planes of a complex density share the pass.  HBM-bound: 8*N^4 bytes per build.
+// which makes two passes over a 16*N^4-byte complex copy.  Here every element of TwoE is read exactly
+// once (see the kernel comment); Re and Im planes of a complex density share the pass.
+// HBM-bound: 8*N^4 bytes per build.
 #include <algorithm>
 #include <string>
 
@@ -25,85 +23,107 @@ __global__ void transpose_kernel(const double *A, int N, double *AT)
     }
 }
 
-template <bool CPLX, bool VEC2>
+// One warp per (p,q): it streams the N rows T[p][x][q][:] (x = 0..N-1, N contiguous doubles each) and keeps
+//     kacc   += T[p][x][q][r] * P[x][r]      -> one cross-lane reduction per warp  -> K[p][q]   (plain store)
+//     jacc_r += T[p][x][q][r] * P[x][p]      -> per lane, no reduction             -> J[q][r]  (+= over p, atomics)
+// J uses (pq|rs) = (rs|pq):  J[q][r] = sum_{p,x} T[p][x][q][r] P[x][p].  Two FMAs per loaded element, no shuffles
+// in the streaming loop; every T element is read exactly once.
+template <bool CPLX, bool VEC2, int NV>
 __global__ void __launch_bounds__(JK_THREADS) jk_incore_kernel(const double *__restrict__ T, int N,
                                                                const double *__restrict__ Pre,
-                                                               const double *__restrict__ Pim,
-                                                               const double *__restrict__ PTre,
-                                                               const double *__restrict__ PTim, double *Jre, double *Jim,
+                                                               const double *__restrict__ Pim, double *Jre, double *Jim,
                                                                double *Kre, double *Kim)
 {
-    __shared__ double s_j[2][JK_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t N2 = (size_t)N * N;
-    for (size_t slab = blockIdx.x; slab < N2; slab += gridDim.x) {
-        const int p = (int)(slab / N), x = (int)(slab % N);
-        const double *M = T + slab * N2;
-        const double *px_re = Pre + (size_t)x * N;
-        const double *px_im = CPLX ? Pim + (size_t)x * N : nullptr;
-        double jre = 0.0, jim = 0.0;
-        for (int q = warp; q < N; q += JK_WARPS) {
-            const double *row = M + (size_t)q * N;
-            const double *ptr = PTre + (size_t)q * N;
-            const double *pti = CPLX ? PTim + (size_t)q * N : nullptr;
-            double kre = 0.0, kim = 0.0;
-            if (VEC2) {
-                const int n2 = N >> 1;
-                const double2 *row2 = reinterpret_cast<const double2 *>(row);
-                const double2 *px2 = reinterpret_cast<const double2 *>(px_re);
-                const double2 *pt2 = reinterpret_cast<const double2 *>(ptr);
-#pragma unroll 2
-                for (int r = lane; r < n2; r += 32) {
-                    const double2 m = __ldcs(row2 + r);       // streamed once: evict-first
-                    const double2 a = px2[r], t = pt2[r];
-                    kre = fma(m.x, a.x, fma(m.y, a.y, kre));
-                    jre = fma(m.x, t.x, fma(m.y, t.y, jre));
-                    if (CPLX) {
-                        const double2 ai = reinterpret_cast<const double2 *>(px_im)[r];
-                        const double2 ti = reinterpret_cast<const double2 *>(pti)[r];
-                        kim = fma(m.x, ai.x, fma(m.y, ai.y, kim));
-                        jim = fma(m.x, ti.x, fma(m.y, ti.y, jim));
-                    }
-                }
-            } else {
-#pragma unroll 2
-                for (int r = lane; r < N; r += 32) {
-                    const double m = __ldcs(row + r);
-                    kre = fma(m, px_re[r], kre);
-                    jre = fma(m, ptr[r], jre);
-                    if (CPLX) {
-                        kim = fma(m, px_im[r], kim);
-                        jim = fma(m, pti[r], jim);
+    constexpr int MAXV = NV;     // per-lane column slots: 32 * NV columns (double2 columns when VEC2)
+    for (size_t pq = (size_t)blockIdx.x * JK_WARPS + warp; pq < N2; pq += (size_t)gridDim.x * JK_WARPS) {
+        const int p = (int)(pq / N), q = (int)(pq % N);
+        const double *base = T + (size_t)p * N2 * N + (size_t)q * N;      // T[p][0][q][0]; next x is +N2
+        double kre = 0.0, kim = 0.0;
+        if (VEC2) {
+            const int n2 = N >> 1;
+            double2 jr[MAXV], ji[MAXV];
+#pragma unroll
+            for (int v = 0; v < MAXV; ++v) { jr[v] = make_double2(0.0, 0.0); ji[v] = make_double2(0.0, 0.0); }
+#pragma unroll 4
+            for (int x = 0; x < N; ++x) {
+                const double2 *row = reinterpret_cast<const double2 *>(base + (size_t)x * N2);
+                const double2 *px = reinterpret_cast<const double2 *>(Pre + (size_t)x * N);
+                const double pxp = Pre[(size_t)x * N + p];
+                const double pxpi = CPLX ? Pim[(size_t)x * N + p] : 0.0;
+#pragma unroll
+                for (int v = 0; v < MAXV; ++v) {
+                    const int r = lane + 32 * v;
+                    if (r < n2) {
+                        const double2 m = __ldcs(row + r);       // streamed once: evict-first
+                        const double2 a = px[r];
+                        kre = fma(m.x, a.x, fma(m.y, a.y, kre));
+                        jr[v].x = fma(m.x, pxp, jr[v].x);
+                        jr[v].y = fma(m.y, pxp, jr[v].y);
+                        if (CPLX) {
+                            const double2 ai = reinterpret_cast<const double2 *>(Pim + (size_t)x * N)[r];
+                            kim = fma(m.x, ai.x, fma(m.y, ai.y, kim));
+                            ji[v].x = fma(m.x, pxpi, ji[v].x);
+                            ji[v].y = fma(m.y, pxpi, ji[v].y);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                kre += __shfl_xor_sync(0xffffffffu, kre, o);
-                if (CPLX) kim += __shfl_xor_sync(0xffffffffu, kim, o);
+            for (int v = 0; v < MAXV; ++v) {
+                const int r = lane + 32 * v;
+                if (r < n2) {
+                    atomicAdd(&Jre[(size_t)q * N + 2 * r], jr[v].x);
+                    atomicAdd(&Jre[(size_t)q * N + 2 * r + 1], jr[v].y);
+                    if (CPLX) {
+                        atomicAdd(&Jim[(size_t)q * N + 2 * r], ji[v].x);
+                        atomicAdd(&Jim[(size_t)q * N + 2 * r + 1], ji[v].y);
+                    }
+                }
             }
-            if (lane == 0) {
-                atomicAdd(&Kre[(size_t)p * N + q], kre);
-                if (CPLX) atomicAdd(&Kim[(size_t)p * N + q], kim);
+        } else {
+            double jr[MAXV], ji[MAXV];
+#pragma unroll
+            for (int v = 0; v < MAXV; ++v) { jr[v] = 0.0; ji[v] = 0.0; }
+#pragma unroll 2
+            for (int x = 0; x < N; ++x) {
+                const double *row = base + (size_t)x * N2;
+                const double *px = Pre + (size_t)x * N;
+                const double pxp = px[p];
+                const double pxpi = CPLX ? Pim[(size_t)x * N + p] : 0.0;
+#pragma unroll
+                for (int v = 0; v < MAXV; ++v) {
+                    const int r = lane + 32 * v;
+                    if (r < N) {
+                        const double m = __ldcs(row + r);
+                        kre = fma(m, px[r], kre);
+                        jr[v] = fma(m, pxp, jr[v]);
+                        if (CPLX) {
+                            kim = fma(m, Pim[(size_t)x * N + r], kim);
+                            ji[v] = fma(m, pxpi, ji[v]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < MAXV; ++v) {
+                const int r = lane + 32 * v;
+                if (r < N) {
+                    atomicAdd(&Jre[(size_t)q * N + r], jr[v]);
+                    if (CPLX) atomicAdd(&Jim[(size_t)q * N + r], ji[v]);
+                }
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            jre += __shfl_xor_sync(0xffffffffu, jre, o);
-            if (CPLX) jim += __shfl_xor_sync(0xffffffffu, jim, o);
+            kre += __shfl_xor_sync(0xffffffffu, kre, o);
+            if (CPLX) kim += __shfl_xor_sync(0xffffffffu, kim, o);
         }
         if (lane == 0) {
-            s_j[0][warp] = jre;
-            s_j[1][warp] = jim;
+            Kre[pq] = kre;            // K[p][q]: single owner, no atomics
+            if (CPLX) Kim[pq] = kim;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double a = 0.0, b = 0.0;
-            for (int w = 0; w < JK_WARPS; ++w) { a += s_j[0][w]; b += s_j[1][w]; }
-            Jre[slab] = a;
-            if (CPLX) Jim[slab] = b;
-        }
-        __syncthreads();
     }
 }
 
@@ -118,26 +138,32 @@ extern "C" int mmdb_jk_incore(int device, const double *TwoE_dev, int N, const d
     cudaStream_t st = (cudaStream_t)stream;
     const size_t N2 = (size_t)N * N;
     const bool cplx = P_im_dev != nullptr;
-    double *PT = nullptr;
-    CU(cudaMallocAsync(&PT, sizeof(double) * N2 * 2, st));
-    transpose_kernel<<<(int)std::min<size_t>((N2 + 255) / 256, 4096), 256, 0, st>>>(P_re_dev, N, PT);
-    if (cplx) transpose_kernel<<<(int)std::min<size_t>((N2 + 255) / 256, 4096), 256, 0, st>>>(P_im_dev, N, PT + N2);
-    CU(cudaMemsetAsync(K_re_dev, 0, sizeof(double) * N2, st));
-    if (cplx) CU(cudaMemsetAsync(K_im_dev, 0, sizeof(double) * N2, st));
+    if (N > 512) return fail(MMDB_ERR_UNSUPPORTED, "mmdb_jk_incore: N > 512 (the dense tensor would not fit one GPU anyway)");
+    CU(cudaMemsetAsync(J_re_dev, 0, sizeof(double) * N2, st));
+    if (cplx) CU(cudaMemsetAsync(J_im_dev, 0, sizeof(double) * N2, st));
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-    const int grid = (int)std::min<size_t>(N2, (size_t)nsm * 8 * 4);
+    const int grid = (int)std::min<size_t>((N2 + JK_WARPS - 1) / JK_WARPS, (size_t)nsm * 16);
     const bool vec2 = (N % 2 == 0) && (((uintptr_t)TwoE_dev | (uintptr_t)P_re_dev | (uintptr_t)P_im_dev) % 16 == 0);
-#define LAUNCH(C, V)                                                                                              \
-    jk_incore_kernel<C, V><<<grid, JK_THREADS, 0, st>>>(TwoE_dev, N, P_re_dev, P_im_dev, PT, PT + N2, J_re_dev, J_im_dev, \
-                                                        K_re_dev, K_im_dev)
+    const int cols = vec2 ? N / 2 : N;
+    const int nv = (cols + 31) / 32;      // column slots per lane, rounded up to a compiled size
+#define LAUNCH(C, V, NVV)                                                                                         \
+    jk_incore_kernel<C, V, NVV><<<grid, JK_THREADS, 0, st>>>(TwoE_dev, N, P_re_dev, P_im_dev, J_re_dev, J_im_dev, K_re_dev, K_im_dev)
+#define LAUNCH_NV(C, V)                                                         \
+    do {                                                                        \
+        if (nv <= 1) LAUNCH(C, V, 1);                                           \
+        else if (nv <= 2) LAUNCH(C, V, 2);                                      \
+        else if (nv <= 4) LAUNCH(C, V, 4);                                      \
+        else if (nv <= 8) LAUNCH(C, V, 8);                                      \
+        else LAUNCH(C, V, 16);                                                  \
+    } while (0)
     if (cplx) {
-        if (vec2) LAUNCH(true, true); else LAUNCH(true, false);
+        if (vec2) LAUNCH_NV(true, true); else LAUNCH_NV(true, false);
     } else {
-        if (vec2) LAUNCH(false, true); else LAUNCH(false, false);
+        if (vec2) LAUNCH_NV(false, true); else LAUNCH_NV(false, false);
     }
+#undef LAUNCH_NV
 #undef LAUNCH
     CU(cudaGetLastError());
-    CU(cudaFreeAsync(PT, st));
     return MMDB_OK;
 }
