@@ -41,6 +41,7 @@ struct PairClass {
     mmdb::PairHdr *hdr_dev = nullptr;
     mmdb::PrimPair *prim_dev = nullptr;
     double *Qs_dev = nullptr;   // [npairs]
+    double *Qmax_dev = nullptr; // [ceil(npairs/256)] maxima of Qs over 256-pair chunks (screening early-exit)
     int *K_dev = nullptr;       // [npairs] primitive pairs per shell pair
     int2 *sh_dev = nullptr;     // [npairs] (shA, shB)
 };

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -114,7 +115,7 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     if (!b) return MMDB_OK;
     cudaSetDevice(b->device);
     for (auto &p : b->pc) {
-        cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.Qs_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
+        cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
     }
     for (auto &t : b->boys_dev) cudaFree(t);
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
@@ -233,6 +234,7 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
         CU(cudaMalloc(&P.hdr_dev, sizeof(PairHdr) * P.npairs));
         CU(cudaMalloc(&P.prim_dev, sizeof(PrimPair) * P.prim.size()));
         CU(cudaMalloc(&P.Qs_dev, sizeof(double) * P.npairs));
+        CU(cudaMalloc(&P.Qmax_dev, sizeof(double) * ((P.npairs + 255) / 256)));
         CU(cudaMalloc(&P.K_dev, sizeof(int) * P.npairs));
         CU(cudaMalloc(&P.sh_dev, sizeof(int2) * P.npairs));
         CU(cudaMemcpy(P.hdr_dev, P.hdr.data(), sizeof(PairHdr) * P.npairs, cudaMemcpyHostToDevice));
@@ -405,6 +407,18 @@ __global__ void dshell_kernel(const double *Dabs, int N, const int *bf0, const i
     }
 }
 
+// maxima of the pair bounds over chunks of 256 consecutive pairs (one warp's columns in the screening kernel)
+__global__ void qs_chunk_max_kernel(const double *Qs, int npairs, double *Qmax)
+{
+    const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (chunk * 256 >= npairs) return;
+    double m = 0.0;
+    for (int i = chunk * 256 + lane; i < min(npairs, chunk * 256 + 256); i += 32) m = fmax(m, Qs[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) Qmax[chunk] = m;
+}
+
 // Shell-level screen -> compact quartet list.
 // Rows are KET pairs j in [row0,row1) (j % nshards == shard), columns are BRA pairs i (i >= j when the
 // two classes coincide).  One block handles one row x 2048 consecutive columns: 8 candidates per thread,
@@ -412,10 +426,11 @@ __global__ void dshell_kernel(const double *Dabs, int N, const int *bf0, const i
 // column order, so consecutive list entries share the ket pair (warp-uniform in the ERI kernels: the
 // inner primitive loop and the J_cd reduction run on broadcast data) and walk the bra pairs.
 struct ScreenArgs {
-    const double *Qs_bra, *Qs_ket;
+    const double *Qs_bra, *Qs_ket, *Qmax_bra;
     const int2 *sh_bra, *sh_ket;
     const int *K_bra, *K_ket;
     int nbra, row0, row1, same_class, shard, nshards, nshell, all_pass;
+    int early;                     // warp-level early exit on the chunk maxima of the bra bounds
     int split;                     // classify survivors: block-digestible entries front-to-back, the rest back-to-front
     int force_slow;                // complex density: everything goes to the second list
     const int *bf0;                // first function index per shell
@@ -459,11 +474,18 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         unsigned long long kk = 0;
         const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
         const bool ketDiag = cd.x == cd.y;
+        // warp-level early exit: this warp's 256 columns cannot pass if even their largest bound fails
+        const int wchunk = (c0 >> 8) + warp;
+        bool warp_live = s.all_pass || !s.early || (wchunk * 256 < s.nbra && !(s.Qmax_bra[wchunk] * qj * dg4 < s.tol));
+        if (!warp_live) {   // candidates are still counted for the statistics
+            const int lo = max(cbase, cstart), hi = min(cbase + SCR_CPT, s.nbra);
+            ncand = hi > lo ? (unsigned)(hi - lo) : 0u;
+        }
 #pragma unroll
         for (int k = 0; k < SCR_CPT; ++k) {
             const int i = cbase + k;
             nsl[k] = 0;
-            bool pass = (i < s.nbra) && (i >= cstart);
+            bool pass = warp_live && (i < s.nbra) && (i >= cstart);
             if (pass) {
                 ++ncand;
                 int2 ab = make_int2(0, 0);
@@ -635,6 +657,7 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
         CHK(launch_eri(b, P.la, P.lb, P.la, P.lb, a, EPI_STORE, 0, st));
         schwarz_extract_kernel<<<(P.npairs + 127) / 128, 128, 0, st>>>(P.hdr_dev, P.npairs, P.la, P.lb, b->scratch_dev,
                                                                        b->nbf, b->Q_dev, b->SQ_dev, P.Qs_dev);
+        qs_chunk_max_kernel<<<((P.npairs + 255) / 256 + 3) / 4, 128, 0, st>>>(P.Qs_dev, P.npairs, P.Qmax_dev);
     }
     CU(cudaGetLastError());
     if (Q_dev) CU(cudaMemcpyAsync(Q_dev, b->Q_dev, N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -649,12 +672,13 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
                       cudaStream_t st)
 {
     ScreenArgs s;
-    s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
+    s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.Qmax_bra = B.Qmax_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
     s.K_bra = B.K_dev; s.K_ket = K.K_dev;
     s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
     s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
     s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = list;
     s.count = b->ctr_dev + CTR_PER_LAUNCH * slot; s.primq = s.count + 1; s.cand = s.count + 2; s.count_slow = s.count + 3; s.nquart = s.count + 4;
+    s.early = getenv("MMDB_SCREEN_NO_EARLY_EXIT") ? 0 : 1;
     s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
     const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(row1 - row0) * ntile;
@@ -886,6 +910,7 @@ extern "C" int mmdb_set_schwarz_host(mmdb_basis *b, const double *Q_tri)
         if (P.npairs == 0) continue;
         schwarz_from_Q_kernel<<<(P.npairs + 127) / 128, 128>>>(P.hdr_dev, P.npairs, P.la, P.lb, N, b->Q_dev, b->SQ_dev,
                                                                 P.Qs_dev);
+        qs_chunk_max_kernel<<<((P.npairs + 255) / 256 + 3) / 4, 128>>>(P.Qs_dev, P.npairs, P.Qmax_dev);
     }
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());

@@ -109,6 +109,17 @@ def test_schwarz_formPT_jk_onee(oracle, golden, cfg):
         assert np.abs(got - g[key]).max() < 1e-12
 
 
+def test_onee_larger_molecule_vs_oracle(oracle):
+    # one-electron enabler at a size the golden fixtures do not cover (many atoms, large Boys arguments)
+    mol = Molecule(*synth.config("benzene_631gss"))
+    Z = [a.charge for a in mol.atoms]
+    xyz = [a.origin for a in mol.atoms]
+    got = mol.engine.onee(Z, xyz, mol.center_of_charge)
+    ref = oracle.onee(mol.bfs, Z, xyz, mol.center_of_charge)
+    for g, r in zip(got, ref):
+        assert np.abs(g - r).max() < 1e-11
+
+
 def test_jk_incore_even_and_odd_sizes(oracle):
     rng = np.random.default_rng(2)
     he2 = "\n0 1\nHe 0.0 0.0 0.0\nHe 0.0 0.0 3.0\n"
