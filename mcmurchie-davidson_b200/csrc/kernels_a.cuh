@@ -369,8 +369,19 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     }
 }
 
+// minimum co-resident CTAs per SM the compiler must allow for (register cap = 65536 / (128 * MINB)):
+// the light classes are latency-bound, so they trade a few registers for more warps in flight
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr int min_blocks()
+{
+    constexpr int L = LA + LB + LC + LD;
+    if (L == 0) return 6;
+    if (L == 1) return 5;
+    return 2;     // measured: tighter caps on the L >= 2 classes only add spills
+}
+
 template <int LA, int LB, int LC, int LD, int EPI>
-__global__ void __launch_bounds__(KA_THREADS) eri_class_kernel(const EriArgs a)
+__global__ void __launch_bounds__(KA_THREADS, min_blocks<LA, LB, LC, LD>()) eri_class_kernel(const EriArgs a)
 {
     constexpr int NCD = ncart(LC) * ncart(LD);
     constexpr int NCDC = chunk_ncd<LA, LB, LC, LD>();
