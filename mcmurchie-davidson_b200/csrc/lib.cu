@@ -445,7 +445,7 @@ struct ScreenArgs {
 };
 
 constexpr int SCR_THREADS = 256;
-constexpr int SCR_CPT = 8;
+constexpr int SCR_CPT = 4;
 constexpr int SCR_TILE = SCR_THREADS * SCR_CPT;
 
 __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
@@ -475,8 +475,13 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
         const bool ketDiag = cd.x == cd.y;
         // warp-level early exit: this warp's 256 columns cannot pass if even their largest bound fails
-        const int wchunk = (c0 >> 8) + warp;
-        bool warp_live = s.all_pass || !s.early || (wchunk * 256 < s.nbra && !(s.Qmax_bra[wchunk] * qj * dg4 < s.tol));
+        // chunk maxima cover 256 consecutive pairs; a warp covers SCR_CPT * 32 of them
+        bool warp_live = s.all_pass || !s.early;
+        {
+            const int first = c0 + warp * (SCR_CPT * 32), last = first + SCR_CPT * 32 - 1;
+            for (int wchunk = first >> 8; wchunk <= (last >> 8); ++wchunk)
+                if (wchunk * 256 < s.nbra && !(s.Qmax_bra[wchunk] * qj * dg4 < s.tol)) warp_live = true;
+        }
         if (!warp_live) {   // candidates are still counted for the statistics
             const int lo = max(cbase, cstart), hi = min(cbase + SCR_CPT, s.nbra);
             ncand = hi > lo ? (unsigned)(hi - lo) : 0u;
