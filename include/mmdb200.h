@@ -133,6 +133,13 @@ int mmdb_eri_dense_host(mmdb_basis *b, double *TwoE_host);
 int mmdb_onee_host(mmdb_basis *b, int natom, const double *Z, const double *xyz, const double *origin,
                    double *S, double *T, double *V, double *M, double *L);
 
+/* ---- post-SCF consumers of the dense tensor (next row) ------------------- */
+/* AO->MO transformation (mmd/postscf.py:21-41) by four cuBLAS DGEMM quarter transformations and the
+ * closed-shell MP2 correlation energy (mmd/postscf.py:59-70).  Row-major (N,N,N,N) tensors; C_dev (N,N)
+ * real MO coefficients (column = orbital); work_dev = N^4 doubles of scratch; e2_host may be NULL. */
+int mmdb_ao2mo_mp2(int device, const double *TwoE_dev, int N, int nocc, const double *C_dev, const double *eps_dev,
+                   double *MO_dev, double *work_dev, double *e2_host, void *stream);
+
 /* ---- utilities --------------------------------------------------------------------------- */
 /* F_0..F_mmax(T[i]) evaluated on the device with the kernels' Boys routine: out[i*(mmax+1)+m]. */
 int mmdb_boys_host(int device, int mmax, int64_t n, const double *T, double *out);

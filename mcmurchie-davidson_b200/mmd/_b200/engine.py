@@ -222,6 +222,26 @@ class Engine(object):
             K += 1j * o[3]
         return J, K
 
+    # ---- AO->MO transformation + MP2 (mmd/postscf.py:21-41, 59-70) ---------------------------------
+    def ao2mo_mp2(self, Cmat, eps, nocc, want_energy=True):
+        """single_bar (N,N,N,N) in the MO basis and the MP2 correlation energy, from the device-resident
+        dense tensor.  Real orbital coefficients only (the caller keeps the host path otherwise)."""
+        torch = _torch()
+        if self.TwoE_dev is None:
+            raise L.MMDBError("ao2mo_mp2: no device-resident TwoE (run the in-core path first)")
+        N = self.N
+        with torch.cuda.device(self.tdev):
+            Cd = torch.from_numpy(np.ascontiguousarray(Cmat, dtype=np.float64)).to(self.tdev)
+            ed = torch.from_numpy(np.ascontiguousarray(eps, dtype=np.float64)).to(self.tdev)
+            MO = torch.empty((N, N, N, N), dtype=torch.float64, device=self.tdev)
+            work = torch.empty((N, N, N, N), dtype=torch.float64, device=self.tdev)
+            e2 = C.c_double(0.0)
+            L.check(self.lib.mmdb_ao2mo_mp2(self.device, L.ptr(self.TwoE_dev), N, int(nocc), L.ptr(Cd), L.ptr(ed), L.ptr(MO),
+                                            L.ptr(work), C.byref(e2) if want_energy else None, self._stream()))
+            del work
+            single_bar = MO.cpu().numpy()
+        return single_bar, (e2.value if want_energy else None)
+
     # ---- direct Fock build (cython/fock.pyx:13-87 formPT) ----------------------------------------
     def _pinned(self, name, shape):
         """Cached page-locked staging buffer (torch tensor + numpy view)."""

@@ -76,6 +76,7 @@ SIGNATURES = {
     "mmdb_schwarz_host": (C.c_int, [_vp, _vp]),
     "mmdb_eri_dense_host": (C.c_int, [_vp, _vp]),
     "mmdb_onee_host": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmdb_ao2mo_mp2": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _dp, _vp]),
     "mmdb_boys_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp]),
     "mmdb_fp64_peak": (C.c_int, [C.c_int, _dp, C.POINTER(C.c_float)]),
     "mmdb_class_flops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -25,11 +25,18 @@ class PostSCF(object):
         complex rotation inside a degenerate orbital set (X = S^-1/2 carries ~1e-17 imaginary noise,
         e.g. CH4) it keeps E(MP2) invariant, where the un-conjugated form would not be."""
         C = self.mol.C
-        Cc = np.conjugate(C)
-        t = np.einsum("pqrs,sS->pqrS", self.mol.TwoE, C, optimize=True)
-        t = np.einsum("pqrS,rR->pqRS", t, Cc, optimize=True)
-        t = np.einsum("pqRS,qQ->pQRS", t, C, optimize=True)
-        self.mol.single_bar = np.einsum("pQRS,pP->PQRS", t, Cc, optimize=True)
+        self._e2_device = None
+        eng = getattr(self.mol, "engine", None)
+        real_orbitals = not np.iscomplexobj(C) or float(np.abs(C.imag).max()) < 1e-13
+        if real_orbitals and eng is not None and getattr(eng, "TwoE_dev", None) is not None and hasattr(eng, "ao2mo_mp2"):
+            # device path: four cuBLAS DGEMM quarter transformations on the resident tensor + MP2 reduction kernel
+            self.mol.single_bar, self._e2_device = eng.ao2mo_mp2(np.real(C), np.real(self.mol.MO), self.mol.nocc)
+        else:
+            Cc = np.conjugate(C)
+            t = np.einsum("pqrs,sS->pqrS", self.mol.TwoE, C, optimize=True)
+            t = np.einsum("pqrS,rR->pqRS", t, Cc, optimize=True)
+            t = np.einsum("pqRS,qQ->pQRS", t, C, optimize=True)
+            self.mol.single_bar = np.einsum("pQRS,pP->PQRS", t, Cc, optimize=True)
         self.mol.norb = self.mol.nbasis * 2
         self._spin = np.eye(2)
         # spin-orbital quantities are O((2N)^4) and only needed for spin_orbital=True: built lazily
@@ -50,6 +57,8 @@ class PostSCF(object):
             for i, j, a, b in product(occ, occ, virt, virt):
                 acc += mol.double_bar[i, j, a, b] ** 2 / (mol.fs[i, i] + mol.fs[j, j] - mol.fs[a, a] - mol.fs[b, b])
             mol.emp2 = 0.25 * acc + mol.energy
+        elif getattr(self, "_e2_device", None) is not None:
+            mol.emp2 = self._e2_device + mol.energy
         else:
             acc = 0.0
             occ, virt = range(mol.nocc), range(mol.nocc, mol.nbasis)

@@ -170,6 +170,25 @@ def test_tight_convergence_is_noise_limited(golden):
     assert mol.is_converged and abs(mol.energy.real - a["energy"]) < E_TOL
 
 
+def test_ao2mo_mp2_device_vs_host(golden):
+    """Device AO->MO (cuBLAS DGEMM quarter transformations) + MP2 kernel against the reference's formulas on the host."""
+    from mmd.postscf import PostSCF
+    for cfg in ("h2o_sto3g", "h2o_ccpvdz"):
+        mol = Molecule(*synth.config(cfg))
+        mol.RHF(doPrint=False)
+        post = PostSCF(mol)
+        assert post._e2_device is not None            # the device path ran
+        C = np.real(mol.C)
+        ref = np.einsum("pqrs,pP,qQ,rR,sS->PQRS", mol.TwoE, C, C, C, C, optimize=True)
+        assert np.abs(mol.single_bar - ref).max() < 1e-11
+        post.MP2()
+        assert abs(mol.emp2.real - float(golden(cfg + ".npz")["emp2"])) < E_TOL
+        dev = mol.emp2.real
+        post._e2_device = None                         # force the host loop of the reference
+        post.MP2()
+        assert abs(mol.emp2.real - dev) < 1e-11
+
+
 def test_degenerate_guess_case_ch4_sto3g(golden):
     # noise-limited trajectory (see tests/test_host_logic.py::test_scf_degenerate_guess_case_is_noise_limited)
     for name in ("ch4_sto3g_incore", "ch4_sto3g_direct"):
