@@ -114,10 +114,15 @@ typedef struct {
  * called on the handle.  G planes must be zeroed by the caller (the call accumulates), which lets
  * shards of one build add into one buffer.  Work is restricted to shard `shard` of `nshards`
  * (static cost-balanced split of bra shell pairs); nshards = 1 does the whole build.
- * flags: bit0 = time each class launch with CUDA events (fills stats->class_ms; synchronises). */
+ * flags: bit0 = time each class launch with CUDA events (fills stats->class_ms; synchronises);
+ *        bit1 = DETERMINISTIC accumulation: contributions are rounded to multiples of 2^-50 and added with 64-bit
+ *               integer atomics, so G is bitwise reproducible for any schedule / shard count.  G then holds scaled
+ *               integers: sum the shards as int64 and finish with mmdb_fixed_to_double. */
 int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const double *dP_im_dev, double tol,
                      double *G_re_dev, double *G_im_dev, int shard, int nshards, int flags,
                      mmdb_fock_stats *stats, void *stream);
+
+int mmdb_fixed_to_double(int device, double *G_dev, int64_t n, void *stream);
 
 /* Host-buffer convenience forms (the reference-facing calls: host numpy in, host numpy out;
  * H2D/D2H inside).  P, P_old, G are complex128 interleaved (N,N) like the reference's arrays;

@@ -94,6 +94,23 @@ __device__ __forceinline__ void red_add_f64(double *p, double v)
 {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 }
+// Accumulation into G on the per-function digestion path.  fixed == 0: FP64 atomics.
+// fixed != 0: DETERMINISTIC mode — the contribution is rounded to a multiple of 2^-50 and added with a
+// 64-bit INTEGER atomic; integer addition is associative, so G is bitwise reproducible for any thread
+// schedule, any shard count and any all-reduce order (|G| < 2^13 is required; a Fock element is O(10)).
+// In deterministic mode the screening kernel sends EVERY quartet to the per-function list, so the block
+// digestion kernels (FP64 atomics, warp-level pre-reduction whose grouping depends on the list order) are
+// not used at all: reproducibility costs speed, it is meant for parity runs.
+constexpr double FIXED_SCALE = 1125899906842624.0;          // 2^50
+__device__ __forceinline__ void red_add_g(int fixed, double *p, double v)
+{
+    if (fixed) {
+        const long long q = __double2ll_rn(v * FIXED_SCALE);
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(q) : "memory");
+    } else {
+        red_add_f64(p, v);
+    }
+}
 __device__ __forceinline__ void prefetch_l1(const void *p)
 {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
@@ -465,8 +482,10 @@ struct DigestArgs {
     const double *dPim;    // Im dP or nullptr
     double *Gre;
     double *Gim;           // or nullptr
+    int fixed;             // deterministic fixed-point accumulation (see red_add_g)
 };
 
+template <bool FIXED>
 __device__ __forceinline__ void digest_fn_quartet(const DigestArgs &g, int i, int j, int k, int l, bool sameAB,
                                                   bool sameCD, bool samePair, double val)
 {
@@ -494,20 +513,20 @@ __device__ __forceinline__ void digest_fn_quartet(const DigestArgs &g, int i, in
     const double e = deg * val;                                            // fock.pyx:74-75
     const double eq = -0.25 * e;
     const double *P = g.dPre;
-    red_add_f64(&g.Gre[i * N + j], __ldg(&P[k * N + l]) * e);                         // fock.pyx:79
-    red_add_f64(&g.Gre[k * N + l], __ldg(&P[i * N + j]) * e);                         // fock.pyx:80
-    red_add_f64(&g.Gre[i * N + k], __ldg(&P[j * N + l]) * eq);                        // fock.pyx:82
-    red_add_f64(&g.Gre[j * N + l], __ldg(&P[i * N + k]) * eq);                        // fock.pyx:83
-    red_add_f64(&g.Gre[i * N + l], __ldg(&P[j * N + k]) * eq);                        // fock.pyx:84
-    red_add_f64(&g.Gre[k * N + j], __ldg(&P[i * N + l]) * eq);                        // fock.pyx:85
+    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + j], __ldg(&P[k * N + l]) * e);                         // fock.pyx:79
+    red_add_g(FIXED ? 1 : 0, &g.Gre[k * N + l], __ldg(&P[i * N + j]) * e);                         // fock.pyx:80
+    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + k], __ldg(&P[j * N + l]) * eq);                        // fock.pyx:82
+    red_add_g(FIXED ? 1 : 0, &g.Gre[j * N + l], __ldg(&P[i * N + k]) * eq);                        // fock.pyx:83
+    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + l], __ldg(&P[j * N + k]) * eq);                        // fock.pyx:84
+    red_add_g(FIXED ? 1 : 0, &g.Gre[k * N + j], __ldg(&P[i * N + l]) * eq);                        // fock.pyx:85
     if (g.dPim != nullptr) {
         const double *Q = g.dPim;
-        red_add_f64(&g.Gim[i * N + j], __ldg(&Q[k * N + l]) * e);
-        red_add_f64(&g.Gim[k * N + l], __ldg(&Q[i * N + j]) * e);
-        red_add_f64(&g.Gim[i * N + k], __ldg(&Q[j * N + l]) * eq);
-        red_add_f64(&g.Gim[j * N + l], __ldg(&Q[i * N + k]) * eq);
-        red_add_f64(&g.Gim[i * N + l], __ldg(&Q[j * N + k]) * eq);
-        red_add_f64(&g.Gim[k * N + j], __ldg(&Q[i * N + l]) * eq);
+        red_add_g(FIXED ? 1 : 0, &g.Gim[i * N + j], __ldg(&Q[k * N + l]) * e);
+        red_add_g(FIXED ? 1 : 0, &g.Gim[k * N + l], __ldg(&Q[i * N + j]) * e);
+        red_add_g(FIXED ? 1 : 0, &g.Gim[i * N + k], __ldg(&Q[j * N + l]) * eq);
+        red_add_g(FIXED ? 1 : 0, &g.Gim[j * N + l], __ldg(&Q[i * N + k]) * eq);
+        red_add_g(FIXED ? 1 : 0, &g.Gim[i * N + l], __ldg(&Q[j * N + k]) * eq);
+        red_add_g(FIXED ? 1 : 0, &g.Gim[k * N + j], __ldg(&Q[i * N + l]) * eq);
     }
 }
 

@@ -296,6 +296,7 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
     }
 }
 
+template <bool FIXED>
 static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, const PairHdr &bh, const PairHdr &kh, bool samePair,
                                                int la, int lb, int lc, int ld, int cd0, int ncdc, const double *vals)
 {
@@ -309,8 +310,8 @@ static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, cons
             const int cd = cd0 + cdi, c = cd / nd, d = cd % nd;
             const double s = sab * ((lc == 2 && (c == 0 || c == 3 || c == 5)) ? 0.57735026918962576451 : 1.0) *
                              ((ld == 2 && (d == 0 || d == 3 || d == 5)) ? 0.57735026918962576451 : 1.0);
-            digest_fn_quartet(dg, bh.bfA + aa, bh.bfB + bb, kh.bfA + c, kh.bfB + d, sameAB, sameCD, samePair,
-                              vals[ab * ncdc + cdi] * s);
+            digest_fn_quartet<FIXED>(dg, bh.bfA + aa, bh.bfB + bb, kh.bfA + c, kh.bfB + d, sameAB, sameCD, samePair,
+                                     vals[ab * ncdc + cdi] * s);
         }
     }
 }
@@ -364,7 +365,8 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
             double tmp[NAB * NCDC];
 #pragma unroll
             for (int x = 0; x < NAB * NCDC; ++x) tmp[x] = out[x];
-            digest_block_slow(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
+            if (a.dg.fixed) digest_block_slow<true>(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
+            else digest_block_slow<false>(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
         }
     }
 }

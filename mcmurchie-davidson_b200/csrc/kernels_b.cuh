@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
             const bool sameAB = (bh.shA == bh.shB), sameCD = (kh.shA == kh.shB);
             const bool samePair = a.same_class && (ij.x == ij.y);
             const int hiB = max(bh.bfA, bh.bfB), hiK = max(kh.bfA, kh.bfB);
-            const bool fast = (a.dg.dPim == nullptr) && !sameAB && !sameCD && (hiB != hiK);
+            const bool fast = (a.dg.dPim == nullptr) && !a.dg.fixed && !sameAB && !sameCD && (hiB != hiK);
             if (fast) {
                 // shell-level digestion for this thread's (c,d): see digest_block in kernels_a.cuh
                 const DigestGeom g = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
@@ -217,9 +217,13 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
                 }
                 red_add_f64(&G[ocd], jcd);
             } else {
-                for (int ab = 0; ab < NAB; ++ab)
-                    digest_fn_quartet(a.dg, bh.bfA + ab / NB, bh.bfB + ab % NB, kh.bfA + c, kh.bfB + d, sameAB, sameCD,
-                                      samePair, out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB)));
+                for (int ab = 0; ab < NAB; ++ab) {
+                    const double v = out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB));
+                    if (a.dg.fixed)
+                        digest_fn_quartet<true>(a.dg, bh.bfA + ab / NB, bh.bfB + ab % NB, kh.bfA + c, kh.bfB + d, sameAB, sameCD, samePair, v);
+                    else
+                        digest_fn_quartet<false>(a.dg, bh.bfA + ab / NB, bh.bfB + ab % NB, kh.bfA + c, kh.bfB + d, sameAB, sameCD, samePair, v);
+                }
             }
         }
     }

@@ -808,7 +808,8 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                 CU(cudaEventCreate(&ln.e1));
                 CU(cudaEventRecord(ln.e0, s1));
             }
-            CHK(run_screen(b, B, K, t.cb == t.ck, t.row0, t.row1, shard, nshards, false, tol, slot, true, dP_im_dev != nullptr,
+            CHK(run_screen(b, B, K, t.cb == t.ck, t.row0, t.row1, shard, nshards, false, tol, slot, true,
+                           dP_im_dev != nullptr || (flags & 2) != 0,
                            (long long)t.cap, list, s1));
             if (timing) CU(cudaEventRecord(ln.em, s1));
             EriArgs a;
@@ -817,6 +818,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             a.list = list; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.same_class = (t.cb == t.ck);
             a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
             a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
+            a.dg.fixed = (flags & 2) ? 1 : 0;
             // block-digestible quartets, then the second list (diagonal-type quartets / complex density)
             CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST, 0, s1));
             a.list = list + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + 3;
@@ -860,6 +862,21 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     }
     for (auto &ln : launches)
         if (ln.e0) { cudaEventDestroy(ln.e0); cudaEventDestroy(ln.em); cudaEventDestroy(ln.e1); }
+    CU(cudaGetLastError());
+    return MMDB_OK;
+}
+
+// deterministic mode: G holds 2^50-scaled 64-bit integers until the (integer) reductions are done
+__global__ void fixed_to_double_kernel(double *G, size_t n)
+{
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x)
+        G[x] = (double)__double_as_longlong(G[x]) * (1.0 / FIXED_SCALE);
+}
+
+extern "C" int mmdb_fixed_to_double(int device, double *G_dev, int64_t n, void *stream)
+{
+    CU(cudaSetDevice(device));
+    fixed_to_double_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, (cudaStream_t)stream>>>(G_dev, (size_t)n);
     CU(cudaGetLastError());
     return MMDB_OK;
 }

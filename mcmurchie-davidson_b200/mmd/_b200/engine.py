@@ -74,6 +74,8 @@ class Engine(object):
         self.TwoE_dev = None
         self.last_stats = None
         self._pin = {}
+        # MMDB_DETERMINISTIC=1: fixed-point integer accumulation of G (bitwise reproducible builds)
+        self.deterministic = os.environ.get("MMDB_DETERMINISTIC", "0") not in ("", "0")
 
     def __del__(self):
         try:
@@ -281,10 +283,16 @@ class Engine(object):
             dP = pin_in.to(self.tdev, non_blocking=True)
             G = torch.zeros((nplane, n, n), dtype=torch.float64, device=self.tdev)
             stats = L.FockStats() if want_stats else None
+            if self.deterministic:
+                flags = int(flags) | 2
             L.check(self.lib.mmdb_fock_direct(self.h, L.ptr(dP[0]), L.ptr(dP[1]) if cplx else None, float(tol), L.ptr(G[0]),
                                               L.ptr(G[1]) if cplx else None, rank, world, int(flags),
                                               C.byref(stats) if want_stats else None, self._stream()))
-            D.allreduce_sum_(G)
+            if self.deterministic:
+                D.allreduce_sum_(G.view(torch.int64))         # exact: integer sums do not depend on the order
+                L.check(self.lib.mmdb_fixed_to_double(self.device, L.ptr(G), G.numel(), self._stream()))
+            else:
+                D.allreduce_sum_(G)
             pin_out.copy_(G, non_blocking=True)
             torch.cuda.current_stream(self.tdev).synchronize()
         self.last_stats = stats.as_dict() if want_stats else None

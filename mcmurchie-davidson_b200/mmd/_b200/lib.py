@@ -72,6 +72,7 @@ SIGNATURES = {
     "mmdb_jk_incore": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmdb_fock_direct": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(FockStats), _vp]),
+    "mmdb_fixed_to_double": (C.c_int, [C.c_int, _vp, C.c_int64, _vp]),
     "mmdb_formPT_host": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, C.POINTER(FockStats)]),
     "mmdb_schwarz_host": (C.c_int, [_vp, _vp]),
     "mmdb_eri_dense_host": (C.c_int, [_vp, _vp]),

@@ -170,6 +170,35 @@ def test_tight_convergence_is_noise_limited(golden):
     assert mol.is_converged and abs(mol.energy.real - a["energy"]) < E_TOL
 
 
+def test_deterministic_mode_is_bitwise_reproducible(oracle, golden):
+    """MMDB_DETERMINISTIC: fixed-point integer accumulation -> identical bits run to run and for any shard split,
+    still within the Fock tolerance of the oracle."""
+    import ctypes as C
+    import torch
+    from mmd._b200 import lib as L
+    g = golden("h2o_ccpvdz.npz")
+    mol = Molecule(*synth.config("h2o_ccpvdz"))
+    eng = mol.engine
+    scr = eng.schwarz()
+    eng.deterministic = True
+    try:
+        Z = np.zeros_like(g["P1"])
+        G1 = eng.formPT(g["P1"], Z, screen=scr, tol=1e-12)
+        G2 = eng.formPT(g["P1"], Z, screen=scr, tol=1e-12)
+        assert np.array_equal(G1, G2)
+        assert np.abs(G1 - g["G1"]).max() < FOCK_TOL
+        # three shards accumulated as integers == the unsharded build, bit for bit
+        N = mol.nbasis
+        re = torch.from_numpy(np.ascontiguousarray(g["P1"].real)).to(eng.tdev)
+        acc = torch.zeros((N, N), dtype=torch.float64, device=eng.tdev)
+        for s in range(3):
+            L.check(eng.lib.mmdb_fock_direct(eng.h, L.ptr(re), None, 1e-12, L.ptr(acc), None, s, 3, 2, None, eng._stream()))
+        L.check(eng.lib.mmdb_fixed_to_double(eng.device, L.ptr(acc), acc.numel(), eng._stream()))
+        assert np.array_equal(acc.cpu().numpy(), G1.real)
+    finally:
+        eng.deterministic = False
+
+
 def test_ao2mo_mp2_device_vs_host(golden):
     """Device AO->MO (cuBLAS DGEMM quarter transformations) + MP2 kernel against the reference's formulas on the host."""
     from mmd.postscf import PostSCF
