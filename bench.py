@@ -245,7 +245,10 @@ def incore_bench(E, L, synth, Molecule, np, torch, C):
             "dense_fill_ms": fill_ms, "unique_integrals_per_s": nuniq / (fill_ms * 1e-3),
             "jk_ms": jk_ms, "fock_builds_per_s": 1e3 / jk_ms,
             "roofline": {"bound": "hbm", "kernel": "jk_incore_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach / hbm_peak, "traffic": None,
+                         "frac": ach / hbm_peak,
+                         # ncu --set full (profiles/r01_ncu_jk_incore_summary.txt): dram read 1.659 GB + write 4 MB per
+                         # launch = the algorithmic 8 N^4 bytes, no re-reads
+                         "traffic": 1.6633e9 if N == 120 else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650"}}
 
 
