@@ -489,36 +489,37 @@ template <bool FIXED>
 __device__ __forceinline__ void digest_fn_quartet(const DigestArgs &g, int i, int j, int k, int l, bool sameAB,
                                                   bool sameCD, bool samePair, double val)
 {
-    // each canonical function quartet i>=j, k>=l, ij>=kl exactly once
-    if (sameAB && i < j) return;
-    if (sameCD && k < l) return;
-    if (i < j) { int t = i; i = j; j = t; }
-    if (k < l) { int t = k; k = l; l = t; }
-    const long long ij = (long long)i * (i + 1) / 2 + j, kl = (long long)k * (k + 1) / 2 + l;
-    if (ij < kl) {
-        if (samePair) return;
-        int t = i; i = k; k = t;
-        t = j; j = l; l = t;
-    }
+    // each canonical function quartet i>=j, k>=l, ij>=kl exactly once (cython/fock.pyx:38-44); written
+    // branch-free up to the final "live" test so that all fourteen loads are in flight together
+    bool live = !(sameAB && i < j) && !(sameCD && k < l);
+    const int ii = max(i, j), jj = min(i, j), kk = max(k, l), ll = min(k, l);
+    const long long ij = (long long)ii * (ii + 1) / 2 + jj, kl = (long long)kk * (kk + 1) / 2 + ll;
+    const bool sw = ij < kl;
+    live = live && !(sw && samePair);
+    i = sw ? kk : ii; j = sw ? ll : jj; k = sw ? ii : kk; l = sw ? jj : ll;
     const int N = g.N;
     const double *D = g.Dabs;
-    double bound = __ldg(&g.SQ[i * N + j]) * __ldg(&g.SQ[k * N + l]);                       // fock.pyx:46-47
-    double dmax = fmax(4.0 * __ldg(&D[i * N + j]), 4.0 * __ldg(&D[k * N + l]));             // fock.pyx:49-54
-    dmax = fmax(dmax, fmax(fmax(__ldg(&D[i * N + k]), __ldg(&D[i * N + l])), fmax(__ldg(&D[j * N + k]), __ldg(&D[j * N + l]))));
+    const double *P = g.dPre;
+    const double sq1 = __ldg(&g.SQ[i * N + j]), sq2 = __ldg(&g.SQ[k * N + l]);
+    const double d_ij = __ldg(&D[i * N + j]), d_kl = __ldg(&D[k * N + l]), d_ik = __ldg(&D[i * N + k]);
+    const double d_il = __ldg(&D[i * N + l]), d_jk = __ldg(&D[j * N + k]), d_jl = __ldg(&D[j * N + l]);
+    const double p_kl = __ldg(&P[k * N + l]), p_ij = __ldg(&P[i * N + j]), p_jl = __ldg(&P[j * N + l]);
+    const double p_ik = __ldg(&P[i * N + k]), p_jk = __ldg(&P[j * N + k]), p_il = __ldg(&P[i * N + l]);
+    double bound = sq1 * sq2;                                               // fock.pyx:46-47
+    const double dmax = fmax(fmax(4.0 * d_ij, 4.0 * d_kl), fmax(fmax(d_ik, d_il), fmax(d_jk, d_jl)));   // fock.pyx:49-54
     bound *= dmax;
-    if (bound < g.tol) return;                                              // fock.pyx:56-57
+    if (!live || bound < g.tol) return;                                     // fock.pyx:56-57
     double deg = (i == j) ? 1.0 : 2.0;                                      // fock.pyx:60-70
     if (k != l) deg *= 2.0;
     if (!(i == k && j == l)) deg *= 2.0;
     const double e = deg * val;                                            // fock.pyx:74-75
     const double eq = -0.25 * e;
-    const double *P = g.dPre;
-    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + j], __ldg(&P[k * N + l]) * e);                         // fock.pyx:79
-    red_add_g(FIXED ? 1 : 0, &g.Gre[k * N + l], __ldg(&P[i * N + j]) * e);                         // fock.pyx:80
-    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + k], __ldg(&P[j * N + l]) * eq);                        // fock.pyx:82
-    red_add_g(FIXED ? 1 : 0, &g.Gre[j * N + l], __ldg(&P[i * N + k]) * eq);                        // fock.pyx:83
-    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + l], __ldg(&P[j * N + k]) * eq);                        // fock.pyx:84
-    red_add_g(FIXED ? 1 : 0, &g.Gre[k * N + j], __ldg(&P[i * N + l]) * eq);                        // fock.pyx:85
+    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + j], p_kl * e);                  // fock.pyx:79
+    red_add_g(FIXED ? 1 : 0, &g.Gre[k * N + l], p_ij * e);                  // fock.pyx:80
+    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + k], p_jl * eq);                 // fock.pyx:82
+    red_add_g(FIXED ? 1 : 0, &g.Gre[j * N + l], p_ik * eq);                 // fock.pyx:83
+    red_add_g(FIXED ? 1 : 0, &g.Gre[i * N + l], p_jk * eq);                 // fock.pyx:84
+    red_add_g(FIXED ? 1 : 0, &g.Gre[k * N + j], p_il * eq);                 // fock.pyx:85
     if (g.dPim != nullptr) {
         const double *Q = g.dPim;
         red_add_g(FIXED ? 1 : 0, &g.Gim[i * N + j], __ldg(&Q[k * N + l]) * e);

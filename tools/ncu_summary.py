@@ -7,7 +7,7 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
-hdr, data = rows[hi], rows[hi + 2:]
+hdr, units, data = rows[hi], rows[hi + 1], rows[hi + 2:]
 col = {n: i for i, n in enumerate(hdr)}
 want = [("ms", "gpu__time_duration.sum"), ("regs", "launch__registers_per_thread"),
         ("warps_act%", "sm__warps_active.avg.pct_of_peak_sustained_active"),
@@ -38,7 +38,8 @@ for r in data:
         v = r[col[b]].replace(",", "")
         try:
             f = float(v)
-            out.append("%s=%s" % (a, ("%.3g" % f)))
+            u = units[col[b]] if b in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum") else ""
+            out.append("%s=%s%s" % (a.replace("_MB", ""), ("%.3g" % f), u))
         except ValueError:
             out.append("%s=%s" % (a, v))
     print(short, " ".join(out))
