@@ -15,14 +15,6 @@ namespace {
 constexpr int JK_THREADS = 256;
 constexpr int JK_WARPS = JK_THREADS / 32;
 
-__global__ void transpose_kernel(const double *A, int N, double *AT)
-{
-    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < (size_t)N * N; x += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = x / N, c = x % N;
-        AT[c * N + r] = A[x];
-    }
-}
-
 // One warp per (p,q): it streams the N rows T[p][x][q][:] (x = 0..N-1, N contiguous doubles each) and keeps
 //     kacc   += T[p][x][q][r] * P[x][r]      -> one cross-lane reduction per warp  -> K[p][q]   (plain store)
 //     jacc_r += T[p][x][q][r] * P[x][p]      -> per lane, no reduction             -> J[q][r]  (+= over p, atomics)

@@ -224,7 +224,10 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
         P.slice_entries = 0;
         for (auto &h : P.hdr) P.slice_entries += (size_t)((h.pnum + BRA_SLICE - 1) / BRA_SLICE);
         if (P.npairs == 0) continue;
-        if ((unsigned)P.npairs > PAIR_MASK) return fail(MMDB_ERR_UNSUPPORTED, "more than 2^24 shell pairs in one class");
+        if ((unsigned)P.npairs > PAIR_MASK) {
+            mmdb_basis_destroy(b);
+            return fail(MMDB_ERR_UNSUPPORTED, "more than 2^24 shell pairs in one class");
+        }
         std::vector<int> K(P.npairs);
         std::vector<int2> shs(P.npairs);
         for (int i = 0; i < P.npairs; ++i) {

@@ -120,6 +120,38 @@ def test_onee_larger_molecule_vs_oracle(oracle):
         assert np.abs(g - r).max() < 1e-11
 
 
+def test_host_buffer_c_abi_entry_points(oracle, golden):
+    """The pure C-ABI host-buffer calls (what a non-Python binding would use, INTEGRATION.md option B):
+    mmdb_schwarz_host, mmdb_set_schwarz_host, mmdb_eri_dense_host, mmdb_formPT_host — numpy in, numpy out."""
+    import ctypes as C
+    from mmd._b200 import lib as L
+    g = golden("h2o_ccpvdz.npz")
+    mol = Molecule(*synth.config("h2o_ccpvdz"))
+    eng = mol.engine
+    N = mol.nbasis
+    lib = eng.lib
+    Q = np.zeros(N * (N + 1) // 2)
+    L.check(lib.mmdb_schwarz_host(eng.h, L.ptr(Q)))
+    assert np.abs(Q - g["screen"]).max() < ERI_TOL
+    T = np.zeros((N,) * 4)
+    L.check(lib.mmdb_eri_dense_host(eng.h, L.ptr(T)))
+    assert np.abs(unique_pack(T) - g["TwoE"]).max() < ERI_TOL
+    scr_flat = np.ascontiguousarray(g["screen"], dtype=np.float64)       # keep alive across the call
+    L.check(lib.mmdb_set_schwarz_host(eng.h, L.ptr(scr_flat)))
+    for P, Po, key in ((g["P1"], np.zeros_like(g["P1"]), "G1"), (g["Pz"], np.zeros_like(g["Pz"]), "G3")):
+        Pc = np.ascontiguousarray(P, dtype=np.complex128)
+        Poc = np.ascontiguousarray(Po, dtype=np.complex128)
+        G = np.zeros((N, N), dtype=np.complex128)
+        stats = L.FockStats()
+        L.check(lib.mmdb_formPT_host(eng.h, L.ptr(Pc.view(np.float64)), L.ptr(Poc.view(np.float64)), 1e-12,
+                                     L.ptr(G.view(np.float64)), C.byref(stats)))
+        assert np.abs(G - g[key]).max() < FOCK_TOL
+        assert stats.quartets > 0 and stats.prim_quartets >= stats.quartets
+    # error convention: non-zero return + message, no exception from C
+    rc = lib.mmdb_eri_shell_quartets(eng.h, 0, 1, 1, None, None, None, 0, None)       # pc_bra < pc_ket is invalid
+    assert rc != 0 and b"pc_bra" in lib.mmdb_last_error()
+
+
 def test_jk_incore_even_and_odd_sizes(oracle):
     rng = np.random.default_rng(2)
     he2 = "\n0 1\nHe 0.0 0.0 0.0\nHe 0.0 0.0 3.0\n"
