@@ -100,6 +100,7 @@ typedef struct {
     int64_t prim_quartets;    /* primitive shell quartets evaluated                              */
     int64_t fn_quartets;      /* contracted basis-function quartets produced                     */
     int64_t slow_quartets;    /* of `quartets`: digested per function (diagonal-type / complex)  */
+    int64_t launches;         /* kernels launched by this call (2 density screens + 3 per class-pair chunk) */
     double model_flops;       /* sum over classes of prim_quartets(class) * F(class), SURVEY §8d */
     int64_t class_quartets[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];
     int64_t class_prim_quartets[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];

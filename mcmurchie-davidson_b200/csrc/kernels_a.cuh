@@ -389,9 +389,14 @@ __global__ void __launch_bounds__(KA_THREADS, min_blocks<LA, LB, LC, LD>()) eri_
     constexpr int NCDC = chunk_ncd<LA, LB, LC, LD>();
     constexpr int NCHUNK = NCD / NCDC;
     extern __shared__ double s_boys[];
-    for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = a.boys_tab[x];
-    __syncthreads();
     const unsigned long long n = a.count_dev ? *a.count_dev : a.n;
+    {   // CTAs without work (short lists, persistent grid) leave before staging the 38 KB Boys table
+        constexpr bool BC = block_chunks<LA, LB, LC, LD>();
+        const unsigned long long first = (BC ? blockIdx.x / NCHUNK : blockIdx.x) * (unsigned long long)blockDim.x;
+        if (first >= n) return;
+    }
+    for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
+    __syncthreads();
     // Block-uniform trip count: every warp stays in the loop (the digestion uses warp shuffles) and, for the
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
     // barrier per quartet so they stream through the code together (one fetch serves all of them).

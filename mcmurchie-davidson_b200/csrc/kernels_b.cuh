@@ -82,14 +82,15 @@ template <int EPI>
 __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a, int la, int lb, int lc, int ld)
 {
     extern __shared__ double s_boys[];
-    for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = a.boys_tab[x];
-    __syncthreads();
     const int NA = ncart(la), NB = ncart(lb), NC = ncart(lc), ND = ncart(ld);
     const int NAB = NA * NB, NCD = NC * ND;
     const int LBRA = la + lb, L = la + lb + lc + ld;
     (void)NC;
     const unsigned long long n = a.count_dev ? *a.count_dev : a.n;
     const unsigned long long total = n * (unsigned long long)NCD;
+    if ((unsigned long long)blockIdx.x * blockDim.x >= total) return;      // no work: skip the table staging
+    for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
+    __syncthreads();
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
         const unsigned long long e = w / NCD;

@@ -839,6 +839,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         CU(cudaMemcpyAsync(ctr.data(), b->ctr_dev, sizeof(unsigned long long) * CTR_PER_LAUNCH * slot, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof(*stats));
+        stats->launches = 2 + 3 * (int64_t)launches.size();
         for (auto &ln : launches) {
             const PairClass &B = b->pc[ln.cb], &K = b->pc[ln.ck];
             const int64_t nq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 4];

@@ -26,6 +26,7 @@ class FockStats(C.Structure):
         ("prim_quartets", C.c_int64),
         ("fn_quartets", C.c_int64),
         ("slow_quartets", C.c_int64),
+        ("launches", C.c_int64),
         ("model_flops", C.c_double),
         ("class_quartets", C.c_int64 * (NCLASS_PAIR * NCLASS_PAIR)),
         ("class_prim_quartets", C.c_int64 * (NCLASS_PAIR * NCLASS_PAIR)),
@@ -34,7 +35,7 @@ class FockStats(C.Structure):
     ]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k in ("candidates", "quartets", "prim_quartets", "fn_quartets", "slow_quartets", "model_flops")}
+        d = {k: getattr(self, k) for k in ("candidates", "quartets", "prim_quartets", "fn_quartets", "slow_quartets", "launches", "model_flops")}
         names = ["ss", "ps", "pp", "ds", "dp", "dd"]
         per = {}
         for cb in range(NCLASS_PAIR):
