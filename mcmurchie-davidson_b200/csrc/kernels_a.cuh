@@ -60,10 +60,12 @@ __host__ __device__ constexpr size_t class_smem_bytes()
 }
 
 // ------------------------------------------------------------------------------------------
-// Shell-level digestion (fast path).  Preconditions, checked by the caller: real density, shells
-// A != B, C != D and the higher-indexed shells of bra and ket differ — then the canonical order
-// i>=j, k>=l, ij>=kl of cython/fock.pyx:38-44 is the same for every function quartet of the block
-// and the degeneracy is 8.  All density / Schwarz elements the block needs are loaded up front
+// Shell-level digestion (fast path).  Preconditions, checked by the caller: real density and the
+// higher-indexed shells of bra and ket differ — then the bra/ket order ij>=kl of cython/fock.pyx:38-44
+// is the same for every function quartet of the block.  With A != B and C != D the degeneracy is 8
+// throughout; a pair on ONE shell (A == B, only in the ss/pp/dd pair classes) keeps the components
+// a >= b (fock.pyx:39: j <= i) with half the weight on a == b (fock.pyx:60-62) — static 0 / 0.5 / 1
+// weights selected by a block-uniform flag.  All density / Schwarz elements the block needs are loaded up front
 // (independent loads, one latency exposure), the six updates of fock.pyx:79-85 are accumulated in
 // registers per destination element, and each destination element receives ONE atomic.
 // Orientation: J blocks are stored [hi,lo]; exchange blocks [canonical-bra fn, canonical-ket fn]
@@ -75,6 +77,7 @@ struct BlockAddr {
 };
 
 struct DigestGeom {
+    bool sameAB, sameCD;              // bra / ket pair on one shell
     BlockAddr ab, cd;                 // J blocks, P and G share the address
     BlockAddr pac, pad, pbc, pbd;     // P reads of the exchange blocks
     BlockAddr gac, gad, gbc, gbd;     // G writes of the exchange blocks
@@ -83,7 +86,8 @@ struct DigestGeom {
 __device__ __forceinline__ DigestGeom make_geom(int N, int bfA, int bfB, int bfC, int bfD)
 {
     DigestGeom g;
-    const bool aHi = bfA > bfB, cHi = bfC > bfD;
+    const bool aHi = bfA >= bfB, cHi = bfC >= bfD;     // one shell twice: the first index is the row (a >= b kept)
+    g.sameAB = bfA == bfB; g.sameCD = bfC == bfD;
     g.ab.base = aHi ? (long long)bfA * N + bfB : (long long)bfB * N + bfA;
     g.ab.s0 = aHi ? N : 1; g.ab.s1 = aHi ? 1 : N;
     g.cd.base = cHi ? (long long)bfC * N + bfD : (long long)bfD * N + bfC;
@@ -163,16 +167,20 @@ __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestG
                 const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
                 const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
                 const double pab4 = 4.0 * fabs(pab);
+                double wab = 1.0;
+                if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
                 double jab = 0.0;
                 sfor<0, NCDC>([&](auto J) {
                     constexpr int cdi = decltype(J)::value;
                     constexpr int cd = CD0 + cdi;
                     constexpr int c = cd / ND, d = cd % ND;
                     constexpr double s8 = 8.0 * sab * comp_scale(LC, c) * comp_scale(LD, d);
+                    double w = wab;
+                    if constexpr (LC == LD) w *= g.sameCD ? (c > d ? 1.0 : (c == d ? 0.5 : 0.0)) : 1.0;
                     double dmax = fmax(pab4, 4.0 * fabs(Pcd[cdi]));
                     dmax = fmax(dmax, fmax(fmax(fabs(Pac[c]), fabs(Pad[d])), fmax(fabs(Pbc[b * NC + c]), fabs(Pbd[b * ND + d]))));
                     const double bound = (qab * Qcd[cdi]) * dmax;
-                    const double e = (bound < tol) ? 0.0 : s8 * out[ab * NCDC + cdi];
+                    const double e = (bound < tol) ? 0.0 : (s8 * w) * out[ab * NCDC + cdi];
                     const double eq = -0.25 * e;
                     jab = fma(Pcd[cdi], e, jab);
                     Jcd[cdi] = fma(pab, e, Jcd[cdi]);
@@ -244,6 +252,10 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
     double *__restrict__ G = dg.Gre;
     const long long ocd = g.cd.base + c * g.cd.s0 + d * g.cd.s1;
     double jcd = 0.0;
+    if (LC == LD && g.sameCD) {      // one shell twice: components c >= d only, half weight on c == d
+        if (c < d) active = false;
+        if (c == d) scd *= 0.5;
+    }
     if (active) {
         const double tol = dg.tol;
         const double pcd = __ldg(&P[ocd]), qcd = __ldg(&SQ[ocd]);
@@ -266,10 +278,12 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
                 constexpr double s8 = 8.0 * comp_scale(LA, a) * comp_scale(LB, b);
                 const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
                 const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
+                double wab = 1.0;
+                if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
                 double dmax = fmax(4.0 * fabs(pab), pcd4);
                 dmax = fmax(dmax, fmax(fmax(fabs(pac), fabs(pad)), fmax(fabs(Pbc[b]), fabs(Pbd[b]))));
                 const double bound = (qab * qcd) * dmax;
-                const double e = (bound < tol) ? 0.0 : (s8 * scd) * out[a * NB + b];
+                const double e = (bound < tol) ? 0.0 : (s8 * wab * scd) * out[a * NB + b];
                 const double eq = -0.25 * e;
                 red_add_f64(&G[oab], pcd * e);
                 jcd = fma(pab, e, jcd);

@@ -476,7 +476,6 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         unsigned nsl[SCR_CPT];
         unsigned long long kk = 0;
         const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
-        const bool ketDiag = cd.x == cd.y;
         // warp-level early exit: this warp's 256 columns cannot pass if even their largest bound fails
         // chunk maxima cover 256 consecutive pairs; a warp covers SCR_CPT * 32 of them
         bool warp_live = s.all_pass || !s.early;
@@ -517,8 +516,8 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                     // one list entry per slice of BRA_SLICE bra primitive pairs (direct builds only)
                     nsl[k] = s.split ? (unsigned)((kb + BRA_SLICE - 1) / BRA_SLICE) : 1u;
                     bool slow = false;
-                    if (s.split)   // block digestion needs A != B, C != D and different leading shells (kernels_a.cuh)
-                        slow = s.force_slow || ketDiag || ab.x == ab.y || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
+                    if (s.split)   // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
+                        slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
                     if (slow) { sbits |= 1u << k; nent_slow += nsl[k]; }
                     else nent_fast += nsl[k];
                 }
