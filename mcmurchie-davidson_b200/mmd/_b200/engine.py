@@ -255,6 +255,28 @@ class Engine(object):
             self._pin[name] = cur
         return cur
 
+    def _fock_direct_planes(self, dP, cplx, tol, want_stats, flags):
+        """dP: device float64 (nplane, n, n) in device order -> un-symmetrised G planes (device), summed
+        over the torch.distributed ranks (one all-reduce, NCCL over NVLink)."""
+        torch = _torch()
+        n = self.Ndev
+        rank, world = D.world()
+        nplane = 2 if cplx else 1
+        G = torch.zeros((nplane, n, n), dtype=torch.float64, device=self.tdev)
+        stats = L.FockStats() if want_stats else None
+        if self.deterministic:
+            flags = int(flags) | 2
+        L.check(self.lib.mmdb_fock_direct(self.h, L.ptr(dP[0]), L.ptr(dP[1]) if cplx else None, float(tol), L.ptr(G[0]),
+                                          L.ptr(G[1]) if cplx else None, rank, world, int(flags),
+                                          C.byref(stats) if want_stats else None, self._stream()))
+        if self.deterministic:
+            D.allreduce_sum_(G.view(torch.int64))         # exact: integer sums do not depend on the order
+            L.check(self.lib.mmdb_fixed_to_double(self.device, L.ptr(G), G.numel(), self._stream()))
+        else:
+            D.allreduce_sum_(G)
+        self._last_stats_raw = stats
+        return G
+
     def formPT(self, P, P_old, screen=None, tol=1e-12, want_stats=True, flags=0):
         """Un-symmetrised G (complex128, user order).  Shards over torch.distributed ranks when a
         process group with world_size > 1 is initialised (one process per GPU) and sums the partial
@@ -265,7 +287,6 @@ class Engine(object):
         P_old = np.asarray(P_old)
         n = self.Ndev
         cplx = (np.iscomplexobj(P) or np.iscomplexobj(P_old)) and not np.array_equal(P.imag, P_old.imag)
-        rank, world = D.world()
         nplane = 2 if cplx else 1
         pin_in, pin_in_np = self._pinned("dP", (nplane, n, n))
         pin_out, pin_out_np = self._pinned("G", (nplane, n, n))
@@ -281,25 +302,53 @@ class Engine(object):
                 pin_in_np[1] = dPd.imag
         with torch.cuda.device(self.tdev):
             dP = pin_in.to(self.tdev, non_blocking=True)
-            G = torch.zeros((nplane, n, n), dtype=torch.float64, device=self.tdev)
-            stats = L.FockStats() if want_stats else None
-            if self.deterministic:
-                flags = int(flags) | 2
-            L.check(self.lib.mmdb_fock_direct(self.h, L.ptr(dP[0]), L.ptr(dP[1]) if cplx else None, float(tol), L.ptr(G[0]),
-                                              L.ptr(G[1]) if cplx else None, rank, world, int(flags),
-                                              C.byref(stats) if want_stats else None, self._stream()))
-            if self.deterministic:
-                D.allreduce_sum_(G.view(torch.int64))         # exact: integer sums do not depend on the order
-                L.check(self.lib.mmdb_fixed_to_double(self.device, L.ptr(G), G.numel(), self._stream()))
-            else:
-                D.allreduce_sum_(G)
+            G = self._fock_direct_planes(dP, cplx, tol, want_stats, flags)
             pin_out.copy_(G, non_blocking=True)
             torch.cuda.current_stream(self.tdev).synchronize()
-        self.last_stats = stats.as_dict() if want_stats else None
+        self.last_stats = self._last_stats_raw.as_dict() if want_stats else None
         out = np.empty((n, n), dtype=np.complex128)
         out.real = pin_out_np[0]
         out.imag = pin_out_np[1] if cplx else 0.0
         return self.table.to_user_matrix(out)
+
+    # ---- device-resident variants for the SCF driver: no host round trip ------
+    @property
+    def supports_device_scf(self):
+        """Device and user function order coincide (always true for Molecule-built basis lists)."""
+        return bool(self.table.identity)
+
+    def formPT_dev(self, P, P_old, screen=None, tol=1e-12, want_stats=False, flags=0):
+        """formPT on device tensors: P, P_old complex128 (N,N) on self.tdev -> un-symmetrised complex128 G."""
+        torch = _torch()
+        if not self.table.identity:
+            raise L.MMDBError("formPT_dev: function order differs between user and device")
+        self._install_screen(screen)
+        with torch.cuda.device(self.tdev):
+            d = P - P_old
+            cplx = bool(d.is_complex() and torch.any(d.imag != 0.0).item())
+            if cplx:
+                dP = torch.stack((d.real, d.imag)).contiguous()
+            else:
+                dP = (d.real if d.is_complex() else d).contiguous().unsqueeze(0)
+            G = self._fock_direct_planes(dP, cplx, tol, want_stats, flags)
+            self.last_stats = self._last_stats_raw.as_dict() if want_stats else None
+            return torch.complex(G[0], G[1] if cplx else torch.zeros_like(G[0]))
+
+    def jk_incore_dev(self, P):
+        """J, K complex128 (N,N) device tensors from the device-resident dense tensor; P complex128 on device."""
+        torch = _torch()
+        if self.TwoE_dev is None:
+            raise L.MMDBError("jk_incore_dev: no device-resident TwoE (call dense() first)")
+        N = self.N
+        with torch.cuda.device(self.tdev):
+            Pre = (P.real if P.is_complex() else P).contiguous()
+            cplx = bool(P.is_complex() and torch.any(P.imag != 0.0).item())
+            Pim = P.imag.contiguous() if cplx else None
+            out = torch.zeros((4, N, N), dtype=torch.float64, device=self.tdev)
+            L.check(self.lib.mmdb_jk_incore(self.device, L.ptr(self.TwoE_dev), N, L.ptr(Pre), L.ptr(Pim), L.ptr(out[0]),
+                                            L.ptr(out[1]) if cplx else None, L.ptr(out[2]),
+                                            L.ptr(out[3]) if cplx else None, self._stream()))
+            return torch.complex(out[0], out[1]), torch.complex(out[2], out[3])
 
     # ---- one-electron integrals (cython/onee.pyx) ------------------------------------------------
     def onee(self, charges, coords, origin):

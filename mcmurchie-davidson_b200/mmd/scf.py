@@ -5,6 +5,8 @@ be compared mode-for-mode; the two Fock-build branches call the B200 engine:
     direct=True   G = formPT(P, P_old, ...)   fused screened ERI + J/K digestion kernels
     direct=False  J, K from one pass over the device-resident dense tensor (mmd/scf.py:97-98)
 """
+import os
+
 import numpy as np
 import scipy.linalg
 from numpy.linalg import multi_dot
@@ -29,6 +31,13 @@ class SCF(object):
             self.incFockRst = False          # True would rebuild G from the full density every step
         self.scrTol = acc2e
         self.build(self.direct)
+
+        # SCF linear algebra on the device: same iteration structure, every matrix stays
+        # in HBM between Fock builds.  MMDB_HOST_SCF=1 keeps the NumPy/SciPy loop below (the engine still
+        # builds G / J,K on the GPU); engines without device tensors (the test oracle) always use it.
+        eng = getattr(self, "engine", None)
+        if eng is not None and getattr(eng, "supports_device_scf", False) and not os.environ.get("MMDB_HOST_SCF"):
+            return self._RHF_device(eng, doPrint, DIIS, conver)
 
         self.P = self.P_old
         self.F = self.Core.astype("complex")
@@ -67,21 +76,125 @@ class SCF(object):
                 if last:
                     print("NOT CONVERGED")
                     break
-                self.is_converged = True
-                FPS = np.dot(self.F, np.dot(self.P, self.S))
-                residual = FPS - self.adj(FPS)
-                self.computeDipole()
-                if doPrint:
-                    print("E(SCF)    = ", "{0:.12f}".format(self.energy.real) + " in " + str(step) + " iterations")
-                    print("  Convergence:")
-                    print("    FPS-SPF  = ", np.linalg.norm(residual))
-                    print("    RMS(P)   = ", "{0:.2e}".format(self.P_RMS.real))
-                    print("    dE(SCF)  = ", "{0:.2e}".format(self.delta_energy.real))
-                    print("  Dipole X = ", "{0:.8f}".format(self.mu[0].real))
-                    print("  Dipole Y = ", "{0:.8f}".format(self.mu[1].real))
-                    print("  Dipole Z = ", "{0:.8f}".format(self.mu[2].real))
-                self.scf_iterations = step
+                self._converged_summary(step, doPrint)
                 break
+
+    def _converged_summary(self, step, doPrint):
+        """Bookkeeping and printed summary of a converged run (mmd/scf.py:62-84 of the reference)."""
+        self.is_converged = True
+        FPS = np.dot(self.F, np.dot(self.P, self.S))
+        residual = FPS - self.adj(FPS)
+        self.computeDipole()
+        if doPrint:
+            print("E(SCF)    = ", "{0:.12f}".format(self.energy.real) + " in " + str(step) + " iterations")
+            print("  Convergence:")
+            print("    FPS-SPF  = ", np.linalg.norm(residual))
+            print("    RMS(P)   = ", "{0:.2e}".format(self.P_RMS.real))
+            print("    dE(SCF)  = ", "{0:.2e}".format(self.delta_energy.real))
+            print("  Dipole X = ", "{0:.8f}".format(self.mu[0].real))
+            print("  Dipole Y = ", "{0:.8f}".format(self.mu[1].real))
+            print("  Dipole Z = ", "{0:.8f}".format(self.mu[2].real))
+        self.scf_iterations = step
+
+    def _RHF_device(self, eng, doPrint, DIIS, conver):
+        """The RHF loop above with every matrix a complex128 torch tensor on the engine's GPU: Fock builds
+        take and return device tensors (formPT_dev / jk_incore_dev), X^T F X, the Hermitian eigenproblem
+        (cuSOLVER through torch.linalg.eigh), the density, the energy, the DIIS error vectors and B matrix
+        run on the device; per iteration only the energy, RMS(P) and the (m+1)x(m+1) DIIS system cross
+        PCIe.  Statement order follows mmd/scf.py:36-84 so energies and iteration counts match mode-for-mode.
+        On exit the reference's attributes (P, F, C, MO, ...) are NumPy arrays again."""
+        import torch
+        dev = eng.tdev
+        c128 = torch.complex128
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=complex))).to(dev)
+
+        n, nocc = self.nbasis, self.nocc
+        with torch.cuda.device(dev):
+            S, X, Core = up(self.S), up(self.X), up(self.Core)
+            XT = X.T                                   # plain transpose, as in the reference
+            P_old = torch.zeros((n, n), dtype=c128, device=dev)
+            P = P_old
+            F = Core.clone()
+            F_old = None
+            G = J = K = None
+            fockSet, errorSet = [], []
+            self.scf_history = []
+            energy = None
+            FO = None
+            for step in range(self.maxiter):
+                if step > 0:
+                    F_old = F
+                    energy_old = energy
+                    if self.direct:                    # buildFock
+                        restart = self.incFockRst
+                        P_ref = torch.zeros_like(P) if restart else P_old
+                        G = eng.formPT_dev(P, P_ref, self.screen, self.scrTol)
+                        G = 0.5 * (G + G.T)
+                        F = (Core if restart else F_old) + G
+                    else:
+                        J, K = eng.jk_incore_dev(P)
+                        G = 2.0 * J - K
+                        F = Core + G
+                    P_old = P
+                    if DIIS:                           # updateDIIS
+                        FPS = F @ (P @ S)
+                        err = X @ ((FPS - FPS.conj().T) @ X)
+                        fockSet.append(F)
+                        errorSet.append(err)
+                        if len(fockSet) > DIIS_DEPTH:
+                            del fockSet[0]
+                            del errorSet[0]
+                        m = len(fockSet)
+                        E = torch.stack(errorSet).reshape(m, -1)
+                        Bmm = (E.conj() @ E.T).real.cpu().numpy()     # tr(e_i^+ e_j)
+                        B = np.zeros((m + 1, m + 1))
+                        B[-1, :] = B[:, -1] = -1.0
+                        B[-1, -1] = 0.0
+                        B[:m, :m] = 0.5 * (Bmm + Bmm.T)
+                        rhs = np.zeros(m + 1)
+                        rhs[-1] = -1.0
+                        weights = np.linalg.solve(B, rhs)
+                        assert np.isclose(sum(weights[:-1]), 1.0)
+                        F_diis = torch.zeros((n, n), dtype=c128, device=dev)
+                        for w, Fk in zip(weights, fockSet):
+                            F_diis += float(w) * Fk
+                        FO = XT @ (F_diis @ X)
+                if not DIIS or step == 0:
+                    FO = XT @ (F @ X)                  # orthoFock
+
+                eps, CO = torch.linalg.eigh(FO)
+                Cm = X @ CO
+                occ = Cm[:, :nocc]
+                P = occ @ occ.conj().T
+                el = torch.sum((Core + F) * P.T)       # einsum("pq,qp")
+                rms = torch.linalg.norm(P - P_old) if step > 0 else torch.zeros((), dtype=torch.float64, device=dev)
+                host = torch.stack((el.real, el.imag, rms.to(torch.float64))).cpu().numpy()
+                self.el_energy = complex(host[0], host[1])
+                energy = self.el_energy + self.nuc_energy
+                self.energy = energy
+                if step > 0:
+                    self.delta_energy = energy - energy_old
+                    self.P_RMS = np.float64(host[2])
+                self.scf_history.append((complex(energy).real, float(np.real(self.P_RMS))))
+                last = step == (self.maxiter - 1)
+                if np.abs(self.P_RMS) < conver or last:
+                    break
+
+            def down(t):
+                return None if t is None else t.cpu().numpy()
+
+            self.P, self.P_old, self.F, self.F_old = down(P), down(P_old), down(F), down(F_old)
+            self.FO, self.CO, self.C, self.MO = down(FO), down(CO), down(Cm), down(eps)
+            self.G, self.J, self.K = down(G), down(J), down(K)
+            if DIIS:
+                self.fockSet = [down(x) for x in fockSet]
+                self.errorSet = [down(x) for x in errorSet]
+        if last:
+            print("NOT CONVERGED")
+            return
+        self._converged_summary(step, doPrint)
 
     # ---- Fock builds -------------------------------------------------------------------------
     def buildFock(self):

@@ -192,6 +192,28 @@ def test_rhf_mp2_end_to_end_vs_reference(golden, name):
         assert abs(mol.emp2.real - a["emp2"]) < E_TOL
 
 
+@pytest.mark.parametrize("direct", [False, True])
+def test_device_scf_loop_equals_host_scf_loop(monkeypatch, direct):
+    """the RHF loop with device-resident linear algebra (default) against the NumPy/SciPy
+    loop (MMDB_HOST_SCF=1) on the same GPU Fock builds: same iteration count, energy, density, orbital energies."""
+    geom, basis = synth.config("h2o_ccpvdz")
+    dev = Molecule(geom, basis)
+    dev.RHF(doPrint=False, direct=direct)
+    monkeypatch.setenv("MMDB_HOST_SCF", "1")
+    host = Molecule(geom, basis)
+    host.RHF(doPrint=False, direct=direct)
+    assert dev.is_converged and host.is_converged
+    assert dev.scf_iterations == host.scf_iterations
+    assert abs(dev.energy.real - host.energy.real) < E_TOL
+    assert np.abs(dev.P - host.P).max() < 1e-8 and np.abs(dev.F - host.F).max() < 1e-8
+    assert np.abs(dev.MO - host.MO).max() < 1e-8
+    for attr in ("P", "F", "C", "MO", "FO", "CO", "G", "P_old"):
+        assert isinstance(getattr(dev, attr), np.ndarray), attr
+    assert np.abs(np.asarray(dev.mu) - np.asarray(host.mu)).max() < 1e-6
+    assert len(dev.scf_history) == len(host.scf_history)
+    assert max(abs(a[0] - b[0]) for a, b in zip(dev.scf_history, host.scf_history)) < 1e-8
+
+
 def test_tight_convergence_is_noise_limited(golden):
     """conver=1e-14 asks RMS(P) to drop below the rounding noise of the Fock build itself: the iteration
     count then depends on summation order (the device reductions use FP64 atomics), so only convergence
