@@ -385,19 +385,31 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     }
 }
 
-// minimum co-resident CTAs per SM the compiler must allow for (register cap = 65536 / (128 * MINB)):
-// the light classes are latency-bound, so they trade a few registers for more warps in flight
+// CTA shape.  The L <= 2 classes run ONE large CTA per SM (as many warps as their register use allows:
+// 24 / 20 / 12 / 12 / 16) instead of several 128-thread CTAs: every CTA stages its own 38.5 KB copy of the
+// Boys table, and five or six copies per SM left the L1 cache with a few tens of KB (ncu: 37% L1 hit rate
+// on the primitive-pair, header and density loads, long-scoreboard stalls on the first use of each load).
+// The L >= 3 classes keep 128-thread CTAs (they synchronise per quartet, see LOCKSTEP below).
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr int ka_threads()
+{
+    constexpr int L = LA + LB + LC + LD;
+    if (L == 0) return 768;                      // 80 registers
+    if (L == 1) return 640;                      // 96 registers
+    if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
+    if (L == 2) return 384;                      // (ps|ps), (pp|ss): <= 170 registers
+    return KA_THREADS;
+}
+
+// minimum co-resident CTAs per SM the compiler must allow for (register cap = 65536 / (threads * MINB))
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr int min_blocks()
 {
-    constexpr int L = LA + LB + LC + LD;
-    if (L == 0) return 6;
-    if (L == 1) return 5;
-    return 2;     // measured: tighter caps on the L >= 2 classes only add spills
+    return (LA + LB + LC + LD <= 2) ? 1 : 2;     // measured: tighter caps on the L >= 3 classes only add spills
 }
 
 template <int LA, int LB, int LC, int LD, int EPI>
-__global__ void __launch_bounds__(KA_THREADS, min_blocks<LA, LB, LC, LD>()) eri_class_kernel(const EriArgs a)
+__global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, LB, LC, LD>()) eri_class_kernel(const EriArgs a)
 {
     constexpr int NCD = ncart(LC) * ncart(LD);
     constexpr int NCDC = chunk_ncd<LA, LB, LC, LD>();
@@ -477,6 +489,7 @@ template <int LA, int LB, int LC, int LD>
 cudaError_t launch_class_impl(const EriArgs &a, int epi, int grid, cudaStream_t st)
 {
     constexpr size_t smem = class_smem_bytes<LA, LB, LC, LD>();
+    constexpr int threads = ka_threads<LA, LB, LC, LD>();
     static int occ[3] = {0, 0, 0};
     if (occ[0] == 0) {
         if (smem > 48 * 1024) {
@@ -485,20 +498,27 @@ cudaError_t launch_class_impl(const EriArgs &a, int epi, int grid, cudaStream_t 
             cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         // persistent grid: as many CTAs as are co-resident (occupancy x SM count); `grid` carries the SM count
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, KA_THREADS, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, KA_THREADS, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, KA_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, threads, smem);
         for (int &o : occ)
             if (o < 1) o = 1;
+        // shared-memory carve-out: just what the resident CTAs need, the rest of the 256 KB stays L1
+        const int pct[3] = {(int)std::min<size_t>(100, (smem * occ[0] + 1024 * occ[0]) * 100 / (228 * 1024) + 3),
+                            (int)std::min<size_t>(100, (smem * occ[1] + 1024 * occ[1]) * 100 / (228 * 1024) + 3),
+                            (int)std::min<size_t>(100, (smem * occ[2] + 1024 * occ[2]) * 100 / (228 * 1024) + 3)};
+        cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct[0]);
+        cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, cudaFuncAttributePreferredSharedMemoryCarveout, pct[1]);
+        cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, cudaFuncAttributePreferredSharedMemoryCarveout, pct[2]);
     }
     constexpr int NCH = block_chunks<LA, LB, LC, LD>() ? ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() : 1;
     auto shape = [&](int o) { return std::max(NCH, (grid * o) / NCH * NCH); };   // multiple of the chunk count
     if (epi == EPI_STORE)
-        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<shape(occ[0]), KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<shape(occ[0]), threads, smem, st>>>(a);
     else if (epi == EPI_DIGEST)
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<shape(occ[1]), KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<shape(occ[1]), threads, smem, st>>>(a);
     else
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW><<<shape(occ[2]), KA_THREADS, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW><<<shape(occ[2]), threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

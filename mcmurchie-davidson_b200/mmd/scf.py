@@ -111,6 +111,8 @@ class SCF(object):
             return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=complex))).to(dev)
 
         n, nocc = self.nbasis, self.nocc
+        trace = bool(os.environ.get("MMDB_SCF_TRACE"))      # per-build (quartets, candidates, ms) in self.fock_trace
+        self.fock_trace = []
         with torch.cuda.device(dev):
             S, X, Core = up(self.S), up(self.X), up(self.Core)
             XT = X.T                                   # plain transpose, as in the reference
@@ -130,7 +132,14 @@ class SCF(object):
                     if self.direct:                    # buildFock
                         restart = self.incFockRst
                         P_ref = torch.zeros_like(P) if restart else P_old
-                        G = eng.formPT_dev(P, P_ref, self.screen, self.scrTol)
+                        if trace:
+                            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            t0.record()
+                        G = eng.formPT_dev(P, P_ref, self.screen, self.scrTol, want_stats=trace)
+                        if trace:
+                            t1.record()
+                            t1.synchronize()
+                            self.fock_trace.append((eng.last_stats["quartets"], eng.last_stats["candidates"], t0.elapsed_time(t1)))
                         G = 0.5 * (G + G.T)
                         F = (Core if restart else F_old) + G
                     else:

@@ -22,3 +22,5 @@ for cfg, direct in runs:
     print("%-16s %-8s N=%4d  E(RHF) = %.10f  iterations %3s  converged %s  wall %.1f s" % (
         cfg, "direct" if direct else "in-core", mol.nbasis, mol.energy.real, getattr(mol, "scf_iterations", None),
         mol.is_converged, dt), flush=True)
+    for it, (q, c, ms) in enumerate(getattr(mol, "fock_trace", []) or []):
+        print("    build %2d: %11d quartets of %11d candidates  %8.3f ms" % (it + 1, q, c, ms), flush=True)
