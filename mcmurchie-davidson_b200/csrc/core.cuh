@@ -142,6 +142,16 @@ __device__ __forceinline__ PairHdr ld_hdr(const PairHdr *p)
 constexpr int BOYS_ROWS = 481;
 constexpr int BOYS_STRIDE = 10;
 constexpr double BOYS_TMAX = 60.0;
+// Class-specialised kernels switch to the asymptotic series as early as their highest order allows: the
+// smallest integer T beyond which sqrt(pi/T)/2 * (2m-1)!!/(2T)^m is within 2e-17 (relative) of F_m(T) for
+// every m <= L (checked against 60-digit hyp1f1).  Fewer lanes take the table branch (in extended systems
+// it runs with a third of the warp active) and only the first boys_rows(L) table rows are staged.
+__host__ __device__ constexpr int boys_tmax_i(int L)
+{
+    constexpr int t[9] = {37, 41, 44, 47, 50, 53, 55, 58, 60};
+    return t[L < 0 ? 0 : (L > 8 ? 8 : L)];
+}
+__host__ __device__ constexpr int boys_rows(int L) { return boys_tmax_i(L) * 8 + 1; }
 
 // 1/sqrt(x) to full double precision without the slow-path branches of the library routine:
 // MUFU.RSQ64H seed (2^-22) + two Newton steps.  x is a sum of exponents or a Boys argument >= 60 here.
@@ -164,7 +174,7 @@ constexpr int BOYS_MAXL = 8;
 template <int L>
 __device__ __forceinline__ void boys_eval(double T, const double *__restrict__ tab, double (&F)[L + 1])
 {
-    if (T < BOYS_TMAX) {
+    if (T < (double)boys_tmax_i(L)) {
         const int row = __double2int_rn(T * 8.0);
         const double *r = tab + row * BOYS_STRIDE;
         const double d = (double)row * 0.125 - T;   // T0 - T, |d| <= 1/16
@@ -384,10 +394,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
 #pragma unroll
         for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
 
-        PrimPair k_next = ld_prim(kp + kh.poff);
-        for (int ik = 0; ik < kh.pnum; ++ik) {
-            const PrimPair k = k_next;
-            if (ik + 1 < kh.pnum) k_next = ld_prim(kp + kh.poff + ik + 1);   // in flight while this one is consumed
+        auto ket_body = [&](const PrimPair &k) {
             const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
             RStore<L, RSMEM> R;
             if constexpr (RSMEM) {
@@ -438,6 +445,29 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
                     });
                 });
             });
+        };
+        // The next ket primitive pair is loaded while the current one is consumed.  The light classes
+        // alternate between two register sets (loop unrolled by two) so the hand-over costs no moves —
+        // the 16 register copies were a fifth of their inner loop; the heavy classes keep one copy of
+        // the (large) loop body.
+        if constexpr (L <= 2) {
+            PrimPair k0 = ld_prim(kp + kh.poff), k1 = k0;
+            for (int ik = 0; ik < kh.pnum; ik += 2) {
+                const bool two = ik + 1 < kh.pnum;
+                if (two) k1 = ld_prim(kp + kh.poff + ik + 1);
+                ket_body(k0);
+                if (two) {
+                    if (ik + 2 < kh.pnum) k0 = ld_prim(kp + kh.poff + ik + 2);
+                    ket_body(k1);
+                }
+            }
+        } else {
+            PrimPair k_next = ld_prim(kp + kh.poff);
+            for (int ik = 0; ik < kh.pnum; ++ik) {
+                const PrimPair k = k_next;
+                if (ik + 1 < kh.pnum) k_next = ld_prim(kp + kh.poff + ik + 1);
+                ket_body(k);
+            }
         }
         // bra Hermite -> Cartesian:  out[ab][cd] += E^ab_t E^ab_u E^ab_v G[tuv][cd]
         // (the bra E table is built here, after the ket primitives, so it is not live across the ket loop)

@@ -54,7 +54,7 @@ __host__ __device__ constexpr bool block_chunks()
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr size_t class_smem_bytes()
 {
-    size_t b = (size_t)BOYS_ROWS * BOYS_STRIDE * sizeof(double);
+    size_t b = (size_t)boys_rows(LA + LB + LC + LD) * BOYS_STRIDE * sizeof(double);
     if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(LA + LB + LC + LD) * KA_THREADS * sizeof(double);
     return b;
 }
@@ -340,7 +340,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     double out[NAB * NCDC];
     if (valid)
         eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS>(
-            bh, a.braP, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + BOYS_ROWS * BOYS_STRIDE + threadIdx.x,
+            bh, a.braP, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + boys_rows(LA + LB + LC + LD) * BOYS_STRIDE + threadIdx.x,
             KA_THREADS, ib0, ib1, out);
     if constexpr (EPI == EPI_STORE) {
         if (valid) {
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, L
         const unsigned long long first = (BC ? blockIdx.x / NCHUNK : blockIdx.x) * (unsigned long long)blockDim.x;
         if (first >= n) return;
     }
-    for (int x = threadIdx.x; x < BOYS_ROWS * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
+    for (int x = threadIdx.x; x < boys_rows(LA + LB + LC + LD) * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
     __syncthreads();
     // Block-uniform trip count: every warp stays in the loop (the digestion uses warp shuffles) and, for the
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
