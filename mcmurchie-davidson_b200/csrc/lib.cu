@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
     __shared__ unsigned long long s_wk[SCR_THREADS / 32];
     __shared__ unsigned s_wcand[SCR_THREADS / 32];
     __shared__ unsigned long long s_base, s_base_slow;
+    __shared__ unsigned short s_slot[SCR_THREADS / 32][SCR_CPT * 32];    // compacted phase-1 survivors per warp
     const int ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(s.row1 - s.row0) * ntile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -469,45 +470,77 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const int cstart = s.same_class ? j : 0;
         if (c0 + SCR_TILE <= cstart) continue;
         const double qj = s.Qs_ket[j];
+        if (!s.all_pass && s.early) {
+            // dead tile (block-uniform test on the chunk maxima): nothing can pass, so skip the scans, barriers
+            // and atomics altogether — only the candidate count is kept for the statistics.  A tile is a
+            // latency chain of ~7 dependent memory round trips; most ket pairs of an extended system are weak
+            // and most of their tiles die here after one.
+            bool tile_live = false;
+            for (int ch = c0 >> 8; ch <= ((c0 + SCR_TILE - 1) >> 8); ++ch)
+                if (ch * 256 < s.nbra && !(s.Qmax_bra[ch] * qj * dg4 < s.tol)) tile_live = true;
+            if (!tile_live) {
+                if (threadIdx.x == 0) {
+                    const int lo = max(c0, cstart), hi = min(c0 + SCR_TILE, s.nbra);
+                    if (hi > lo) atomicAdd(s.cand, (unsigned long long)(hi - lo));
+                }
+                continue;
+            }
+        }
         const int2 cd = s.sh_ket[j];
         const unsigned long long kj = (unsigned long long)s.K_ket[j];
-        const int cbase = c0 + threadIdx.x * SCR_CPT;
+        // Two phases per warp (128 consecutive columns).  Phase 1: the cheap density-independent bound on
+        // all columns, lane-strided (coalesced), survivors compacted into a per-warp slot array in column
+        // order.  Phase 2: the six-block density test, slicing and list classification run on the compacted
+        // survivors only, lane n taking survivors [n R, n R + R) — in extended systems ~10% of the columns
+        // pass phase 1, so the expensive part no longer runs with mostly idle lanes.
+        const int wbase = c0 + warp * (SCR_CPT * 32);
         unsigned bits = 0, sbits = 0, ncand = 0, nent_fast = 0, nent_slow = 0;
         unsigned nsl[SCR_CPT];
+        int col[SCR_CPT];
         unsigned long long kk = 0;
         const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
-        // warp-level early exit: this warp's 256 columns cannot pass if even their largest bound fails
-        // chunk maxima cover 256 consecutive pairs; a warp covers SCR_CPT * 32 of them
+        // warp-level early exit: this warp's columns cannot pass if even their largest bound fails
+        // (chunk maxima cover 256 consecutive pairs; a warp covers SCR_CPT * 32 of them)
         bool warp_live = s.all_pass || !s.early;
         {
-            const int first = c0 + warp * (SCR_CPT * 32), last = first + SCR_CPT * 32 - 1;
+            const int first = wbase, last = first + SCR_CPT * 32 - 1;
             for (int wchunk = first >> 8; wchunk <= (last >> 8); ++wchunk)
                 if (wchunk * 256 < s.nbra && !(s.Qmax_bra[wchunk] * qj * dg4 < s.tol)) warp_live = true;
         }
-        if (!warp_live) {   // candidates are still counted for the statistics
-            const int lo = max(cbase, cstart), hi = min(cbase + SCR_CPT, s.nbra);
-            ncand = hi > lo ? (unsigned)(hi - lo) : 0u;
-        }
+        unsigned total = 0;
 #pragma unroll
         for (int k = 0; k < SCR_CPT; ++k) {
-            const int i = cbase + k;
+            const int off = k * 32 + lane;
+            const int i = wbase + off;
+            const bool cand = (i < s.nbra) && (i >= cstart);
+            ncand += cand ? 1u : 0u;            // candidates are counted for the statistics even when the warp exits early
+            bool p1 = cand && warp_live;
+            if (p1 && !s.all_pass) p1 = !(s.Qs_bra[i] * qj * dg4 < s.tol);
+            const unsigned m = __ballot_sync(0xffffffffu, p1);
+            if (p1) s_slot[warp][total + __popc(m & ((1u << lane) - 1u))] = (unsigned short)off;
+            total += __popc(m);
+        }
+        __syncwarp();
+        const unsigned per = (total + 31u) >> 5;      // survivors per lane (<= SCR_CPT)
+#pragma unroll
+        for (int k = 0; k < SCR_CPT; ++k) {
             nsl[k] = 0;
-            bool pass = warp_live && (i < s.nbra) && (i >= cstart);
-            if (pass) {
-                ++ncand;
+            col[k] = 0;
+            const unsigned n = lane * per + k;
+            if ((unsigned)k < per && n < total) {
+                const int i = wbase + s_slot[warp][n];
+                col[k] = i;
+                bool pass = true;
                 int2 ab = make_int2(0, 0);
                 if (!s.all_pass) {
                     const double qq = s.Qs_bra[i] * qj;
-                    pass = !(qq * dg4 < s.tol);
-                    if (pass) {
-                        ab = s.sh_bra[i];
-                        const double *DS = s.DS;
-                        const int ns = s.nshell;
-                        double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
-                        dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
-                                               fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
-                        pass = !(qq * dmax < s.tol);
-                    }
+                    ab = s.sh_bra[i];
+                    const double *DS = s.DS;
+                    const int ns = s.nshell;
+                    double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
+                    dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
+                                           fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
+                    pass = !(qq * dmax < s.tol);
                 }
                 if (pass) {
                     bits |= 1u << k;
@@ -568,7 +601,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
             for (int k = 0; k < SCR_CPT; ++k)
                 if (bits & (1u << k)) {
                     for (unsigned sl = 0; sl < nsl[k]; ++sl) {
-                        const uint2 ent = make_uint2((unsigned)(cbase + k) | (sl << SLICE_SHIFT), (unsigned)j);
+                        const uint2 ent = make_uint2((unsigned)col[k] | (sl << SLICE_SHIFT), (unsigned)j);
                         if (sbits & (1u << k)) s.list[spos--] = ent;
                         else s.list[pos++] = ent;
                     }
