@@ -103,17 +103,19 @@ class SCF(object):
         run on the device; per iteration only the energy, RMS(P) and the (m+1)x(m+1) DIIS system cross
         PCIe.  Statement order follows mmd/scf.py:36-84 so energies and iteration counts match mode-for-mode.
         On exit the reference's attributes (P, F, C, MO, ...) are NumPy arrays again."""
+        import contextlib
         import torch
         dev = eng.tdev
         c128 = torch.complex128
+        on_gpu = dev.type == "cuda"          # the CPU test-suite drives this loop with host tensors
 
         def up(a):
             return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=complex))).to(dev)
 
         n, nocc = self.nbasis, self.nocc
-        trace = bool(os.environ.get("MMDB_SCF_TRACE"))      # per-build (quartets, candidates, ms) in self.fock_trace
+        trace = on_gpu and bool(os.environ.get("MMDB_SCF_TRACE"))      # per-build (quartets, candidates, ms) in self.fock_trace
         self.fock_trace = []
-        with torch.cuda.device(dev):
+        with (torch.cuda.device(dev) if on_gpu else contextlib.nullcontext()):
             S, X, Core = up(self.S), up(self.X), up(self.Core)
             XT = X.T                                   # plain transpose, as in the reference
             P_old = torch.zeros((n, n), dtype=c128, device=dev)

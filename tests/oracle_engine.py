@@ -40,14 +40,35 @@ class OracleEngine(object):
         return O.ERI_batch(self.fb, idx)
 
 
-def install(monkeypatch):
+class OracleTensorEngine(OracleEngine):
+    """OracleEngine that also offers the device-tensor entry points of Engine (formPT_dev, jk_incore_dev) on
+    CPU torch tensors, so the CPU suite can drive the device-resident SCF loop (mmd/scf.py:_RHF_device)."""
+    supports_device_scf = True
+
+    def __init__(self, bfs):
+        import torch
+        OracleEngine.__init__(self, bfs)
+        self.tdev = torch.device("cpu")
+
+    def formPT_dev(self, P, P_old, screen=None, tol=1e-12, want_stats=False, flags=0):
+        import torch
+        G = O.formPT(P.numpy(), P_old.numpy(), self.fb, self.N, screen, tol)
+        return torch.from_numpy(np.ascontiguousarray(G))
+
+    def jk_incore_dev(self, P):
+        import torch
+        J, K = O.jk_incore(self.TwoE, np.ascontiguousarray(P.numpy()))
+        return torch.from_numpy(np.ascontiguousarray(J)), torch.from_numpy(np.ascontiguousarray(K))
+
+
+def install(monkeypatch, engine_cls=None):
     """Route engine_for() of the drop-in package to the oracle for the duration of a test."""
     cache = {}
 
     def engine_for(bfs):
         key = tuple(id(b) for b in bfs)
         if key not in cache:
-            cache[key] = OracleEngine(bfs)
+            cache[key] = (engine_cls or OracleEngine)(bfs)
             cache[key]._keep = list(bfs)
         return cache[key]
 

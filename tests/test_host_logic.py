@@ -176,6 +176,30 @@ def test_tight_convergence_is_noise_limited(monkeypatch, golden):
     assert mol.is_converged and abs(mol.energy.real - a["energy"]) < 1e-9
 
 
+@pytest.mark.parametrize("direct", [False, True])
+def test_device_resident_scf_loop_matches_host_loop(monkeypatch, direct):
+    """mmd/scf.py:_RHF_device (torch tensors, eigh/DIIS/energy on the tensor device) against the NumPy/SciPy loop,
+    both fed by the oracle: same trajectory, iteration count, energy and final matrices (CPU tensors here; the
+    GPU suite repeats it on the device)."""
+    import oracle_engine
+    from mmd._b200 import synth
+    from mmd.molecule import Molecule
+    oracle_engine.install(monkeypatch)
+    host = Molecule(synth.water(), "sto-3g")
+    host.RHF(doPrint=False, direct=direct)
+    oracle_engine.install(monkeypatch, oracle_engine.OracleTensorEngine)
+    dev = Molecule(synth.water(), "sto-3g")
+    dev.RHF(doPrint=False, direct=direct)
+    assert dev.is_converged and host.is_converged and dev.scf_iterations == host.scf_iterations
+    assert abs(dev.energy.real - host.energy.real) < 1e-10
+    assert len(dev.scf_history) == len(host.scf_history)
+    assert max(abs(a[0] - b[0]) for a, b in zip(dev.scf_history, host.scf_history)) < 1e-9
+    for attr in ("P", "F", "MO", "G", "P_old"):
+        assert isinstance(getattr(dev, attr), np.ndarray)
+        assert np.abs(getattr(dev, attr) - getattr(host, attr)).max() < 1e-8, attr
+    assert np.abs(np.asarray(dev.mu) - np.asarray(host.mu)).max() < 1e-7
+
+
 def test_printed_summary_format(monkeypatch, capsys):
     oracle_engine.install(monkeypatch)
     from mmd.molecule import Molecule
