@@ -72,7 +72,7 @@ __host__ __device__ constexpr size_t class_smem_bytes()
 // except (lo of canonical bra, hi of canonical ket) which the reference stores transposed (G[k,j]).
 // ------------------------------------------------------------------------------------------
 struct BlockAddr {
-    long long base;   // element offset of (0,0)
+    long long base;   // element offset of (0,0)  (64-bit on purpose: 32-bit offsets compiled to slower address code)
     int s0, s1;       // strides of the first / second block index
 };
 
@@ -260,7 +260,7 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
         const double tol = dg.tol;
         const double pcd = __ldg(&P[ocd]), qcd = __ldg(&SQ[ocd]);
         const double pcd4 = 4.0 * fabs(pcd);
-        double Pbc[NB], Pbd[NB], Kbc[NB], Kbd[NB];
+        double Pbc[NB], Pbd[NB], Kbc[NB], Kbd[NB], Mb[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             Pbc[b] = __ldg(&P[g.pbc.base + b * g.pbc.s0 + c * g.pbc.s1]);
@@ -268,11 +268,14 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
             Kbc[b] = 0.0;
             Kbd[b] = 0.0;
         }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) Mb[b] = fmax(fabs(Pbc[b]), fabs(Pbd[b]));      // shared by every a
         sfor<0, NA>([&](auto A_) {
             constexpr int a = decltype(A_)::value;
             const double pac = __ldg(&P[g.pac.base + a * g.pac.s0 + c * g.pac.s1]);
             const double pad = __ldg(&P[g.pad.base + a * g.pad.s0 + d * g.pad.s1]);
             double kac = 0.0, kad = 0.0;
+            const double ma = fmax(pcd4, fmax(fabs(pac), fabs(pad)));                // shared by every b
             sfor<0, NB>([&](auto B_) {
                 constexpr int b = decltype(B_)::value;
                 constexpr double s8 = 8.0 * comp_scale(LA, a) * comp_scale(LB, b);
@@ -280,8 +283,7 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
                 const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
                 double wab = 1.0;
                 if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
-                double dmax = fmax(4.0 * fabs(pab), pcd4);
-                dmax = fmax(dmax, fmax(fmax(fabs(pac), fabs(pad)), fmax(fabs(Pbc[b]), fabs(Pbd[b]))));
+                const double dmax = fmax(4.0 * fabs(pab), fmax(ma, Mb[b]));
                 const double bound = (qab * qcd) * dmax;
                 const double e = (bound < tol) ? 0.0 : (s8 * wab * scd) * out[a * NB + b];
                 const double eq = -0.25 * e;
@@ -395,7 +397,7 @@ __host__ __device__ constexpr int ka_threads()
 {
     constexpr int L = LA + LB + LC + LD;
     if (L == 0) return 768;                      // 80 registers
-    if (L == 1) return 640;                      // 96 registers
+    if (L == 1) return 640;                      // 96 registers (768 threads at 80 registers: slower)
     if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
     if (L == 2) return 384;                      // (ps|ps), (pp|ss): <= 170 registers
     return KA_THREADS;

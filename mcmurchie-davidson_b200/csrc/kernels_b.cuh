@@ -171,8 +171,11 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
             const bool sameAB = (bh.shA == bh.shB), sameCD = (kh.shA == kh.shB);
             const bool samePair = a.same_class && (ij.x == ij.y);
             const int hiB = max(bh.bfA, bh.bfB), hiK = max(kh.bfA, kh.bfB);
-            const bool fast = (a.dg.dPim == nullptr) && !a.dg.fixed && !sameAB && !sameCD && (hiB != hiK);
-            if (fast) {
+            // block digestion needs a real density and different leading shells; one-shell pairs keep the
+            // components a >= b (c >= d) with half weight on the diagonal (see digest_block in kernels_a.cuh)
+            const bool fast = (a.dg.dPim == nullptr) && !a.dg.fixed && (hiB != hiK);
+            const double wcd = !sameCD ? 1.0 : (c > d ? 1.0 : (c == d ? 0.5 : 0.0));
+            if (fast && wcd != 0.0) {
                 // shell-level digestion for this thread's (c,d): see digest_block in kernels_a.cuh
                 const DigestGeom g = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
                 const double *__restrict__ P = a.dg.dPre;
@@ -199,7 +202,8 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
                         double dmax = fmax(4.0 * fabs(pab), pcd4);
                         dmax = fmax(dmax, fmax(fmax(fabs(pac), fabs(pad)), fmax(fabs(Pbc[b]), fabs(Pbd[b]))));
                         const double bound = (qab * qcd) * dmax;
-                        const double sc = 8.0 * scd * comp_scale_rt(la, aa) * comp_scale_rt(lb, b);
+                        const double wab = !sameAB ? 1.0 : (aa > b ? 1.0 : (aa == b ? 0.5 : 0.0));
+                        const double sc = 8.0 * (wab * wcd) * scd * comp_scale_rt(la, aa) * comp_scale_rt(lb, b);
                         const double e = (bound < tol) ? 0.0 : sc * out[ab];
                         const double eq = -0.25 * e;
                         red_add_f64(&G[oab], pcd * e);
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
                     red_add_f64(&G[g.gbd.base + b * g.gbd.s0 + d * g.gbd.s1], Kbd[b]);
                 }
                 red_add_f64(&G[ocd], jcd);
-            } else {
+            } else if (!fast) {
                 for (int ab = 0; ab < NAB; ++ab) {
                     const double v = out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB));
                     if (a.dg.fixed)
