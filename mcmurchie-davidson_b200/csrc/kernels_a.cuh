@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, L
     // Block-uniform trip count: every warp stays in the loop (the digestion uses warp shuffles) and, for the
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
     // barrier per quartet so they stream through the code together (one fetch serves all of them).
-    constexpr bool LOCKSTEP = (LA + LB + LC + LD >= 3);
+    constexpr bool LOCKSTEP = (LA + LB + LC + LD >= 4);
     // Chunked classes: the ket-component chunk is a property of the CTA (blockIdx.x % NCHUNK), not a serial
     // loop inside the thread.  Each CTA then executes the code of ONE chunk for many quartets, so its
     // instruction working set is 1/NCHUNK of the kernel and stays cache-resident (ncu: stall_no_instruction
