@@ -51,11 +51,39 @@ __host__ __device__ constexpr bool block_chunks()
     return ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() >= 2;
 }
 
+// CTA shape.  The L <= 2 classes run ONE large CTA per SM (as many warps as their register use allows:
+// 24 / 20 / 12 / 12 / 16) instead of several 128-thread CTAs: every CTA stages its own 38.5 KB copy of the
+// Boys table, and five or six copies per SM left the L1 cache with a few tens of KB (ncu: 37% L1 hit rate
+// on the primitive-pair, header and density loads, long-scoreboard stalls on the first use of each load).
+// The L >= 3 classes keep 128-thread CTAs (they synchronise per quartet, see LOCKSTEP below).
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr int ka_threads()
+{
+    constexpr int L = LA + LB + LC + LD;
+    if (L == 0) return 768;                      // 80 registers
+    if (L == 1) return 640;                      // 96 registers (768 threads at 80 registers: slower)
+    if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
+    if (L == 2) return 384;                      // (ps|ps), (pp|ss): <= 170 registers
+    // lock-step classes, measured per class: one 8-warp CTA per SM (ONE instruction stream per SM, fetched once
+    // for eight warps) wins for (pp|pp) (ds|pp) (dp|dp) (dd|ps) (dd|pp) (dd|ds); (ds|ds) (dp|ps) (dp|pp) (dp|ds)
+    // prefer two 4-warp CTAs (two chunks in flight hide each other's barrier and load stalls)
+    if (L >= 4 && L <= 6 && !(LA == 2 && LB == 1 && !(LC == 2 && LD == 1)) && !(LA == 2 && LB == 0 && LC == 2)) return 256;
+    return KA_THREADS;
+}
+
+// minimum co-resident CTAs per SM the compiler must allow for (register cap = 65536 / (threads * MINB))
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr int min_blocks()
+{
+    constexpr int L = LA + LB + LC + LD;
+    return (L <= 2 || ka_threads<LA, LB, LC, LD>() == 256) ? 1 : 2;     // measured: tighter caps on the L >= 3 classes only add spills
+}
+
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr size_t class_smem_bytes()
 {
     size_t b = (size_t)boys_rows(LA + LB + LC + LD) * BOYS_STRIDE * sizeof(double);
-    if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(LA + LB + LC + LD) * KA_THREADS * sizeof(double);
+    if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(LA + LB + LC + LD) * ka_threads<LA, LB, LC, LD>() * sizeof(double);
     return b;
 }
 
@@ -343,7 +371,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     if (valid)
         eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS>(
             bh, a.braP, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + boys_rows(LA + LB + LC + LD) * BOYS_STRIDE + threadIdx.x,
-            KA_THREADS, ib0, ib1, out);
+            ka_threads<LA, LB, LC, LD>(), ib0, ib1, out);
     if constexpr (EPI == EPI_STORE) {
         if (valid) {
             double *o = a.out + e * (unsigned long long)(NAB * NCD);
@@ -385,29 +413,6 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
             else digest_block_slow<false>(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
         }
     }
-}
-
-// CTA shape.  The L <= 2 classes run ONE large CTA per SM (as many warps as their register use allows:
-// 24 / 20 / 12 / 12 / 16) instead of several 128-thread CTAs: every CTA stages its own 38.5 KB copy of the
-// Boys table, and five or six copies per SM left the L1 cache with a few tens of KB (ncu: 37% L1 hit rate
-// on the primitive-pair, header and density loads, long-scoreboard stalls on the first use of each load).
-// The L >= 3 classes keep 128-thread CTAs (they synchronise per quartet, see LOCKSTEP below).
-template <int LA, int LB, int LC, int LD>
-__host__ __device__ constexpr int ka_threads()
-{
-    constexpr int L = LA + LB + LC + LD;
-    if (L == 0) return 768;                      // 80 registers
-    if (L == 1) return 640;                      // 96 registers (768 threads at 80 registers: slower)
-    if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
-    if (L == 2) return 384;                      // (ps|ps), (pp|ss): <= 170 registers
-    return KA_THREADS;
-}
-
-// minimum co-resident CTAs per SM the compiler must allow for (register cap = 65536 / (threads * MINB))
-template <int LA, int LB, int LC, int LD>
-__host__ __device__ constexpr int min_blocks()
-{
-    return (LA + LB + LC + LD <= 2) ? 1 : 2;     // measured: tighter caps on the L >= 3 classes only add spills
 }
 
 template <int LA, int LB, int LC, int LD, int EPI>
