@@ -71,7 +71,7 @@ __device__ __forceinline__ void sfor(F &&f)
 // ------------------------------------------------------------------------------------------
 struct __align__(16) PrimPair {   // one primitive pair of a shell pair, 64 B
     double Px, Py, Pz, p;          // Gaussian product centre, total exponent
-    double cc;                     // c_a c_b exp(-mu|AB|^2) * sqrt(2) pi^(5/4) / p
+    double cc;                     // c_a c_b exp(-mu|AB|^2) * sqrt(2) pi^(5/4) / p^(3/2)  (the extra 1/sqrt(p): see prim_R)
     double PAx, PAy, PAz;          // P - A   (P - B = PA + (A - B))
 };
 
@@ -171,35 +171,42 @@ constexpr int BOYS_MAXL = 8;
 // ------------------------------------------------------------------------------------------
 // Boys function  (replaces scipy hyp1f1 of cython/util.pxi:54-55)
 // ------------------------------------------------------------------------------------------
+// table branch: valid for T < boys_tmax_i(L) (+ rounding)
+template <int L>
+__device__ __forceinline__ void boys_table(double T, const double *__restrict__ tab, double (&F)[L + 1])
+{
+    const int row = __double2int_rn(T * 8.0);
+    const double *r = tab + row * BOYS_STRIDE;
+    const double d = (double)row * 0.125 - T;   // T0 - T, |d| <= 1/16
+    double f = r[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) f = fma(f, d, r[k]);
+    F[L] = f;
+    if constexpr (L > 0) {
+        // exp(-T) = exp(-T0) * exp(d)
+        double e = 2.48015873015873015873e-05;   // 1/8!
+        e = fma(e, d, 1.98412698412698412698e-04);
+        e = fma(e, d, 1.38888888888888888889e-03);
+        e = fma(e, d, 8.33333333333333333333e-03);
+        e = fma(e, d, 4.16666666666666666667e-02);
+        e = fma(e, d, 1.66666666666666666667e-01);
+        e = fma(e, d, 0.5);
+        e = fma(e, d, 1.0);
+        e = fma(e, d, 1.0);
+        e *= r[9];
+        const double t2 = T + T;
+        sfor<0, L>([&](auto I) {
+            constexpr int m = L - decltype(I)::value;     // m = L .. 1
+            F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
+        });
+    }
+}
+
 template <int L>
 __device__ __forceinline__ void boys_eval(double T, const double *__restrict__ tab, double (&F)[L + 1])
 {
     if (T < (double)boys_tmax_i(L)) {
-        const int row = __double2int_rn(T * 8.0);
-        const double *r = tab + row * BOYS_STRIDE;
-        const double d = (double)row * 0.125 - T;   // T0 - T, |d| <= 1/16
-        double f = r[8];
-#pragma unroll
-        for (int k = 7; k >= 0; --k) f = fma(f, d, r[k]);
-        F[L] = f;
-        if constexpr (L > 0) {
-            // exp(-T) = exp(-T0) * exp(d)
-            double e = 2.48015873015873015873e-05;   // 1/8!
-            e = fma(e, d, 1.98412698412698412698e-04);
-            e = fma(e, d, 1.38888888888888888889e-03);
-            e = fma(e, d, 8.33333333333333333333e-03);
-            e = fma(e, d, 4.16666666666666666667e-02);
-            e = fma(e, d, 1.66666666666666666667e-01);
-            e = fma(e, d, 0.5);
-            e = fma(e, d, 1.0);
-            e = fma(e, d, 1.0);
-            e *= r[9];
-            const double t2 = T + T;
-            sfor<0, L>([&](auto I) {
-                constexpr int m = L - decltype(I)::value;     // m = L .. 1
-                F[m - 1] = fma(t2, F[m], e) * (1.0 / (2 * m - 1));
-            });
-        }
+        boys_table<L>(T, tab, F);
     } else {
         const double rt = fast_rsqrt(T);
         F[0] = 0.88622692545275801365 * rt;                   // sqrt(pi)/2 / sqrt(T)
@@ -344,19 +351,39 @@ __device__ __forceinline__ void build_R_impl(RS &R, const double (&Fs)[L + 1], d
 }
 
 // Boys + prefactor scaling + R recursion for one primitive quartet.
+// ccb, cck are the pair coefficients DIVIDED by sqrt(p) (PrimPair::cc).  With that normalisation the
+// large-T branch — the common one in extended systems — needs neither alpha nor T:
+//     s (-2 alpha)^m F_m(T)  ->  ccb cck sqrt(pi)/2 * (-1)^m (2m-1)!! / |PQ|^(2m+1)        (T >= T_max(L))
+// i.e. ONE reciprocal square root (of |PQ|^2) and a product chain; the branch is taken on
+// p q |PQ|^2 >= T_max (p+q), which needs no division either.  The table branch pays one extra rsqrt
+// (sqrt(alpha)) to undo the normalisation.
 template <int L, class RS>
 __device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, double cck, double X, double Y, double Z,
                                        const double *__restrict__ boys_tab)
 {
-    const double rs = fast_rsqrt(pb + pk);   // one reciprocal square root serves 1/(p+q) and 1/sqrt(p+q)
-    const double alpha = pb * pk * (rs * rs);
-    const double T = alpha * (X * X + Y * Y + Z * Z);
+    const double R2 = X * X + Y * Y + Z * Z;
+    const double pp = pb * pk, ps = pb + pk;
+    const double c2 = ccb * cck;
     double Fs[L + 1];
-    boys_eval<L>(T, boys_tab, Fs);
-    double s = ccb * cck * rs;            // 2 pi^2.5 /(p q sqrt(p+q)) * c's * K's
-    const double m2a = -2.0 * alpha;
+    if (pp * R2 >= (double)boys_tmax_i(L) * ps) {
+        const double ri = fast_rsqrt(R2);
+        Fs[0] = (0.88622692545275801365 * c2) * ri;
+        if constexpr (L > 0) {
+            const double nr2 = -(ri * ri);
+            sfor<0, L>([&](auto I) {
+                constexpr int m = decltype(I)::value;
+                Fs[m + 1] = ((2 * m + 1) * nr2) * Fs[m];
+            });
+        }
+    } else {
+        const double rs = fast_rsqrt(ps);        // one reciprocal square root serves 1/(p+q) and 1/sqrt(p+q)
+        const double alpha = pp * (rs * rs);
+        boys_table<L>(alpha * R2, boys_tab, Fs);
+        double s = c2 * (alpha * fast_rsqrt(alpha));     // ccb cck sqrt(p q) / sqrt(p+q)
+        const double m2a = -2.0 * alpha;
 #pragma unroll
-    for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
+        for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
+    }
     build_R_impl<L>(R, Fs, X, Y, Z);
 }
 

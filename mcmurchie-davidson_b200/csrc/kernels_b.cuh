@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
                 double Fs[KB_MAXL + 1];
                 boys_eval_rt(L, T, s_boys, Fs);
                 {
-                    double s = b.cc * k.cc * rs;
+                    double s = b.cc * k.cc * sqrt(b.p * k.p) * rs;      // PrimPair::cc carries 1/sqrt(p)
                     const double m2a = -2.0 * alpha;
                     for (int nn = 0; nn <= L; ++nn) { Fs[nn] *= s; s *= m2a; }
                 }

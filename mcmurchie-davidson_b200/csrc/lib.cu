@@ -202,7 +202,7 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
                     q.Py = (ea * sa.y + eb * sb.y) / p;
                     q.Pz = (ea * sa.z + eb * sb.z) / p;
                     q.PAx = q.Px - sa.x; q.PAy = q.Py - sa.y; q.PAz = q.Pz - sa.z;
-                    q.cc = c2 * K * SQRT2_PI54 / p;
+                    q.cc = c2 * K * SQRT2_PI54 / (p * std::sqrt(p));    // divided by sqrt(p): see prim_R (core.cuh)
                     t.pp.push_back(q);
                 }
             if (t.pp.empty()) continue;
