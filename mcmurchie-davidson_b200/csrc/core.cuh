@@ -178,22 +178,21 @@ __device__ __forceinline__ void boys_table(double T, const double *__restrict__ 
     const int row = __double2int_rn(T * 8.0);
     const double *r = tab + row * BOYS_STRIDE;
     const double d = (double)row * 0.125 - T;   // T0 - T, |d| <= 1/16
-    double f = r[8];
-#pragma unroll
-    for (int k = 7; k >= 0; --k) f = fma(f, d, r[k]);
-    F[L] = f;
+    // degree-8 polynomials by Estrin's scheme (dependent depth 4 instead of 8): the table branch runs with a
+    // minority of the lanes and its latency, not its instruction count, is what the rest of the warp waits for
+    const double d2 = d * d, d4 = d2 * d2;
+    {
+        const double a01 = fma(r[1], d, r[0]), a23 = fma(r[3], d, r[2]), a45 = fma(r[5], d, r[4]), a67 = fma(r[7], d, r[6]);
+        const double b0 = fma(a23, d2, a01), b1 = fma(a67, d2, a45);
+        F[L] = fma(fma(r[8], d4, b1), d4, b0);
+    }
     if constexpr (L > 0) {
         // exp(-T) = exp(-T0) * exp(d)
-        double e = 2.48015873015873015873e-05;   // 1/8!
-        e = fma(e, d, 1.98412698412698412698e-04);
-        e = fma(e, d, 1.38888888888888888889e-03);
-        e = fma(e, d, 8.33333333333333333333e-03);
-        e = fma(e, d, 4.16666666666666666667e-02);
-        e = fma(e, d, 1.66666666666666666667e-01);
-        e = fma(e, d, 0.5);
-        e = fma(e, d, 1.0);
-        e = fma(e, d, 1.0);
-        e *= r[9];
+        const double a01 = 1.0 + d, a23 = fma(1.66666666666666666667e-01, d, 0.5);
+        const double a45 = fma(8.33333333333333333333e-03, d, 4.16666666666666666667e-02);
+        const double a67 = fma(1.98412698412698412698e-04, d, 1.38888888888888888889e-03);
+        const double b0 = fma(a23, d2, a01), b1 = fma(a67, d2, a45);
+        const double e = fma(fma(2.48015873015873015873e-05, d4, b1), d4, b0) * r[9];
         const double t2 = T + T;
         sfor<0, L>([&](auto I) {
             constexpr int m = L - decltype(I)::value;     // m = L .. 1
@@ -387,6 +386,23 @@ __device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, 
     build_R_impl<L>(R, Fs, X, Y, Z);
 }
 
+// asymptotic branch only (caller has checked p q |PQ|^2 >= T_max (p+q)); c2 = ccb * cck
+template <int L, class RS>
+__device__ __forceinline__ void prim_R_asym(RS &R, double c2, double R2, double X, double Y, double Z)
+{
+    double Fs[L + 1];
+    const double ri = fast_rsqrt(R2);
+    Fs[0] = (0.88622692545275801365 * c2) * ri;
+    if constexpr (L > 0) {
+        const double nr2 = -(ri * ri);
+        sfor<0, L>([&](auto I) {
+            constexpr int m = decltype(I)::value;
+            Fs[m + 1] = ((2 * m + 1) * nr2) * Fs[m];
+        });
+    }
+    build_R_impl<L>(R, Fs, X, Y, Z);
+}
+
 // out-of-line copy for the shared-memory variant: the (long) recursion is emitted once per kernel
 // instead of once per ket-component chunk
 template <int L>
@@ -421,20 +437,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
 #pragma unroll
         for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
 
-        auto ket_body = [&](const PrimPair &k) {
-            const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
-            RStore<L, RSMEM> R;
-            if constexpr (RSMEM) {
-                R.base = r_smem;
-                R.stride = r_stride;
-                // a quartet with ONE primitive quartet keeps its R table in shared memory across the
-                // ket-component chunks: only the first chunk builds it
-                if (!SERIAL_CHUNKS || CD0 == 0 || (ib1 - ib0) * kh.pnum != 1)
-                    prim_R_smem<L>(r_smem, r_stride, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
-            } else {
-                prim_R<L>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
-            }
-
+        auto ket_transform = [&](const auto &R, const PrimPair &k) {
             ETab<LC, LD> Ek;
             {
                 const double QC[3] = {k.PAx, k.PAy, k.PAz};
@@ -473,6 +476,44 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
                 });
             });
         };
+        auto ket_body = [&](const PrimPair &k) {
+            const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
+            RStore<L, RSMEM> R;
+            if constexpr (RSMEM) {
+                R.base = r_smem;
+                R.stride = r_stride;
+                // a quartet with ONE primitive quartet keeps its R table in shared memory across the
+                // ket-component chunks: only the first chunk builds it
+                if (!SERIAL_CHUNKS || CD0 == 0 || (ib1 - ib0) * kh.pnum != 1)
+                    prim_R_smem<L>(r_smem, r_stride, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
+            } else {
+                prim_R<L>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
+            }
+            ket_transform(R, k);
+        };
+        // Two ket primitives at once (L <= 1 only).  These kernels are latency-bound: ~5 warps per scheduler, and
+        // one primitive quartet is essentially ONE dependent chain (|PQ|^2 -> rsqrt -> F_m -> R -> G), so the
+        // FP64 pipe idles between dependent instructions.  When both primitive quartets are on the branch-free
+        // asymptotic path for every converged lane, the two chains are emitted in one basic block and the
+        // compiler interleaves them; otherwise the two bodies run one after the other as before.
+        auto ket_body2 = [&](const PrimPair &ka, const PrimPair &kc) {
+            const double Xa = b.Px - ka.Px, Ya = b.Py - ka.Py, Za = b.Pz - ka.Pz;
+            const double Xc = b.Px - kc.Px, Yc = b.Py - kc.Py, Zc = b.Pz - kc.Pz;
+            const double R2a = Xa * Xa + Ya * Ya + Za * Za, R2c = Xc * Xc + Yc * Yc + Zc * Zc;
+            const double tm = (double)boys_tmax_i(L);
+            const bool asym = ((b.p * ka.p) * R2a >= tm * (b.p + ka.p)) && ((b.p * kc.p) * R2c >= tm * (b.p + kc.p));
+            const unsigned act = __activemask();
+            if (__all_sync(act, asym)) {
+                RStore<L, false> Ra, Rc;
+                prim_R_asym<L>(Ra, b.cc * ka.cc, R2a, Xa, Ya, Za);
+                prim_R_asym<L>(Rc, b.cc * kc.cc, R2c, Xc, Yc, Zc);
+                ket_transform(Ra, ka);
+                ket_transform(Rc, kc);
+            } else {
+                ket_body(ka);
+                ket_body(kc);
+            }
+        };
         // The next ket primitive pair is loaded while the current one is consumed.  The light classes
         // alternate between two register sets (loop unrolled by two) so the hand-over costs no moves —
         // the 16 register copies were a fifth of their inner loop; the heavy classes keep one copy of
@@ -482,10 +523,20 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
             for (int ik = 0; ik < kh.pnum; ik += 2) {
                 const bool two = ik + 1 < kh.pnum;
                 if (two) k1 = ld_prim(kp + kh.poff + ik + 1);
-                ket_body(k0);
-                if (two) {
-                    if (ik + 2 < kh.pnum) k0 = ld_prim(kp + kh.poff + ik + 2);
-                    ket_body(k1);
+                if constexpr (L <= 1 && !RSMEM) {
+                    if (two) {
+                        const PrimPair ka = k0;
+                        if (ik + 2 < kh.pnum) k0 = ld_prim(kp + kh.poff + ik + 2);
+                        ket_body2(ka, k1);
+                    } else {
+                        ket_body(k0);
+                    }
+                } else {
+                    ket_body(k0);
+                    if (two) {
+                        if (ik + 2 < kh.pnum) k0 = ld_prim(kp + kh.poff + ik + 2);
+                        ket_body(k1);
+                    }
                 }
             }
         } else {
