@@ -123,6 +123,26 @@ __device__ __forceinline__ PrimPair ld_prim(const PrimPair *p)
     r.Px = a.x; r.Py = a.y; r.Pz = b.x; r.p = b.y; r.cc = c.x; r.PAx = c.y; r.PAy = d.x; r.PAz = d.y;
     return r;
 }
+// Bra-side primitive pairs are read from a structure-of-arrays copy: field f of primitive k of pair i lives at
+// S[f * N + row[k] + i], row[k] = number of (pair, primitive) slots of the primitives before k (pairs are sorted
+// by primitive count, so primitive k exists for a PREFIX of the pairs and the rows need no padding).  The lanes
+// of a warp walk consecutive bra pairs, so each of the eight loads touches a couple of 128-byte lines instead of
+// thirty-two (the 64-byte records of different pairs are pnum * 64 bytes apart): ncu showed the L1 data pipe
+// of the light classes at 70 % with a third of its wavefronts coming from these loads.
+struct BraSrc {
+    const double *S;
+    const long long *row;
+    long long N;
+    unsigned pair;
+};
+__device__ __forceinline__ PrimPair ld_prim_soa(const BraSrc &src, int k)
+{
+    const double *q = src.S + (__ldg(src.row + k) + (long long)src.pair);
+    PrimPair r;
+    r.Px = __ldg(q); r.Py = __ldg(q + src.N); r.Pz = __ldg(q + 2 * src.N); r.p = __ldg(q + 3 * src.N);
+    r.cc = __ldg(q + 4 * src.N); r.PAx = __ldg(q + 5 * src.N); r.PAy = __ldg(q + 6 * src.N); r.PAz = __ldg(q + 7 * src.N);
+    return r;
+}
 __device__ __forceinline__ PairHdr ld_hdr(const PairHdr *p)
 {
     const int4 *qi = reinterpret_cast<const int4 *>(p);
@@ -418,7 +438,7 @@ __device__ __noinline__ void prim_R_smem(double *base, int stride, double pb, do
 // out[ab*NCDC + cdi] accumulates (ab|cd) WITHOUT the per-component normalisation.
 // ------------------------------------------------------------------------------------------
 template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SERIAL_CHUNKS>
-__device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const PrimPair *__restrict__ bp,
+__device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraSrc &bsrc,
                                                    const PairHdr &kh, const PrimPair *__restrict__ kp,
                                                    const double *__restrict__ boys_tab, double *r_smem, int r_stride,
                                                    int ib0, int ib1, double (&out)[ncart(LA) * ncart(LB) * NCDC])
@@ -432,7 +452,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const Prim
     for (int x = 0; x < NAB * NCDC; ++x) out[x] = 0.0;
 
     for (int ib = ib0; ib < ib1; ++ib) {       // [ib0,ib1): this entry's slice of the bra primitive pairs
-        const PrimPair b = ld_prim(bp + bh.poff + ib);
+        const PrimPair b = ld_prim_soa(bsrc, ib);
         double G[NHB * NCDC];
 #pragma unroll
         for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
@@ -642,7 +662,10 @@ __device__ __forceinline__ void digest_fn_quartet(const DigestArgs &g, int i, in
 // Arguments of the ERI kernels (both families).
 struct EriArgs {
     const PairHdr *braH;
-    const PrimPair *braP;
+    const PrimPair *braP;         // array-of-structures copy (generic kernel)
+    const double *braS;           // structure-of-arrays copy of the bra primitive pairs (class kernels), see BraSrc
+    const long long *braRow;
+    long long braN;
     const PairHdr *ketH;
     const PrimPair *ketP;
     const uint2 *list;            // (bra pair, ket pair) per entry; entry e lives at list[e * list_step]

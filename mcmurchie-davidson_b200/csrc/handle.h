@@ -40,6 +40,8 @@ struct PairClass {
     std::vector<mmdb::PrimPair> prim;
     mmdb::PairHdr *hdr_dev = nullptr;
     mmdb::PrimPair *prim_dev = nullptr;
+    double *prim_soa_dev = nullptr;      // [8 fields][nprimpairs]: field f of primitive k of pair i at f*nprimpairs + row[k] + i
+    long long *prim_row_dev = nullptr;   // [max pnum] row offsets of the structure-of-arrays copy
     double *Qs_dev = nullptr;   // [npairs]
     double *Qmax_dev = nullptr; // [ceil(npairs/256)] maxima of Qs over 256-pair chunks (screening early-exit)
     int *K_dev = nullptr;       // [npairs] primitive pairs per shell pair

@@ -361,7 +361,7 @@ static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, cons
 }
 
 template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC, bool SERIAL_CHUNKS>
-__device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, bool valid, const PairHdr &bh,
+__device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, unsigned ibra, bool valid, const PairHdr &bh,
                                           const PairHdr &kh, const double *boys_tab, bool samePair, bool ket_uniform,
                                           int ib0, int ib1)
 {
@@ -370,7 +370,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     double out[NAB * NCDC];
     if (valid)
         eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS>(
-            bh, a.braP, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + boys_rows(LA + LB + LC + LD) * BOYS_STRIDE + threadIdx.x,
+            bh, BraSrc{a.braS, a.braRow, a.braN, ibra}, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + boys_rows(LA + LB + LC + LD) * BOYS_STRIDE + threadIdx.x,
             ka_threads<LA, LB, LC, LD>(), ib0, ib1, out);
     if constexpr (EPI == EPI_STORE) {
         if (valid) {
@@ -469,11 +469,11 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, L
                 ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid);
             }
             if constexpr (chsel >= 0) {
-                run_chunk<LA, LB, LC, LD, EPI, chsel * NCDC, NCDC, false>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
+                run_chunk<LA, LB, LC, LD, EPI, chsel * NCDC, NCDC, false>(a, e, ij.x, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
             } else {
                 sfor<0, NCHUNK>([&](auto CH) {
                     constexpr int ch = decltype(CH)::value;
-                    run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC, true>(a, e, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
+                    run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC, true>(a, e, ij.x, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
                 });
             }
         }

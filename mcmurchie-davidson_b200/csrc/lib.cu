@@ -115,7 +115,7 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     if (!b) return MMDB_OK;
     cudaSetDevice(b->device);
     for (auto &p : b->pc) {
-        cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
+        cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.prim_soa_dev); cudaFree(p.prim_row_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
     }
     for (auto &t : b->boys_dev) cudaFree(t);
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
@@ -242,6 +242,28 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
         CU(cudaMalloc(&P.sh_dev, sizeof(int2) * P.npairs));
         CU(cudaMemcpy(P.hdr_dev, P.hdr.data(), sizeof(PairHdr) * P.npairs, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(P.prim_dev, P.prim.data(), sizeof(PrimPair) * P.prim.size(), cudaMemcpyHostToDevice));
+        {   // structure-of-arrays copy for the bra side (see BraSrc in core.cuh); pairs are sorted by pnum (desc),
+            // so primitive k exists for the first n_k pairs and row k holds exactly those
+            const int kmax = P.hdr[0].pnum;
+            const long long nprim = (long long)P.prim.size();
+            std::vector<long long> row(kmax + 1, 0);
+            for (int k = 0; k < kmax; ++k) {
+                long long nk = 0;
+                while (nk < P.npairs && P.hdr[nk].pnum > k) ++nk;
+                row[k + 1] = row[k] + nk;
+            }
+            std::vector<double> soa((size_t)8 * nprim);
+            for (int i = 0; i < P.npairs; ++i)
+                for (int k = 0; k < P.hdr[i].pnum; ++k) {
+                    const PrimPair &q = P.prim[P.hdr[i].poff + k];
+                    const double f[8] = {q.Px, q.Py, q.Pz, q.p, q.cc, q.PAx, q.PAy, q.PAz};
+                    for (int x = 0; x < 8; ++x) soa[(size_t)x * nprim + row[k] + i] = f[x];
+                }
+            CU(cudaMalloc(&P.prim_soa_dev, sizeof(double) * soa.size()));
+            CU(cudaMalloc(&P.prim_row_dev, sizeof(long long) * kmax));
+            CU(cudaMemcpy(P.prim_soa_dev, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(P.prim_row_dev, row.data(), sizeof(long long) * kmax, cudaMemcpyHostToDevice));
+        }
         CU(cudaMemset(P.Qs_dev, 0, sizeof(double) * P.npairs));
         CU(cudaMemcpy(P.K_dev, K.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(P.sh_dev, shs.data(), sizeof(int2) * P.npairs, cudaMemcpyHostToDevice));
@@ -669,7 +691,7 @@ extern "C" int mmdb_eri_shell_quartets(mmdb_basis *b, int pc_bra, int pc_ket, in
     PairClass &B = b->pc[pc_bra], &K = b->pc[pc_ket];
     EriArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+    a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
     a.list = b->list_dev; a.list_step = 1; a.count_dev = nullptr; a.n = (unsigned long long)n; a.out = out_dev;
     a.same_class = (pc_bra == pc_ket);
     return launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, impl, st);
@@ -692,7 +714,7 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
         diag_list_kernel<<<(P.npairs + 255) / 256, 256, 0, st>>>(P.npairs, b->list_dev);
         EriArgs a;
         std::memset(&a, 0, sizeof(a));
-        a.braH = P.hdr_dev; a.braP = P.prim_dev; a.ketH = P.hdr_dev; a.ketP = P.prim_dev;
+        a.braH = P.hdr_dev; a.braP = P.prim_dev; a.braS = P.prim_soa_dev; a.braRow = P.prim_row_dev; a.braN = P.nprimpairs; a.ketH = P.hdr_dev; a.ketP = P.prim_dev;
         a.list = b->list_dev; a.list_step = 1; a.n = (unsigned long long)P.npairs; a.out = b->scratch_dev; a.same_class = 1;
         CHK(launch_eri(b, P.la, P.lb, P.la, P.lb, a, EPI_STORE, 0, st));
         schwarz_extract_kernel<<<(P.npairs + 127) / 128, 128, 0, st>>>(P.hdr_dev, P.npairs, P.la, P.lb, b->scratch_dev,
@@ -757,7 +779,7 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
                 CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, b->list_dev, st));
                 EriArgs a;
                 std::memset(&a, 0, sizeof(a));
-                a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+                a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
                 a.list = b->list_dev; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.out = b->scratch_dev;
                 a.same_class = (cb == ck);
                 CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, 0, st));
@@ -849,7 +871,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             if (timing) CU(cudaEventRecord(ln.em, s1));
             EriArgs a;
             std::memset(&a, 0, sizeof(a));
-            a.braH = B.hdr_dev; a.braP = B.prim_dev; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+            a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
             a.list = list; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.same_class = (t.cb == t.ck);
             a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
             a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
