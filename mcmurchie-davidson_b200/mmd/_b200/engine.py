@@ -245,12 +245,13 @@ class Engine(object):
         return single_bar, (e2.value if want_energy else None)
 
     # ---- direct Fock build (cython/fock.pyx:13-87 formPT) ----------------------------------------
-    def _pinned(self, name, shape):
+    def _pinned(self, name, shape, dtype=float):
         """Cached page-locked staging buffer (torch tensor + numpy view)."""
         torch = _torch()
         cur = self._pin.get(name)
-        if cur is None or tuple(cur[0].shape) != tuple(shape):
-            t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        tdt = torch.complex128 if dtype is complex else torch.float64
+        if cur is None or tuple(cur[0].shape) != tuple(shape) or cur[0].dtype != tdt:
+            t = torch.empty(shape, dtype=tdt, pin_memory=True)
             cur = (t, t.numpy())
             self._pin[name] = cur
         return cur
@@ -280,36 +281,32 @@ class Engine(object):
     def formPT(self, P, P_old, screen=None, tol=1e-12, want_stats=True, flags=0):
         """Un-symmetrised G (complex128, user order).  Shards over torch.distributed ranks when a
         process group with world_size > 1 is initialised (one process per GPU) and sums the partial
-        G matrices with one all-reduce (NCCL over NVLink)."""
+        G matrices with one all-reduce (NCCL over NVLink).
+
+        Host side: ONE pass over the inputs (dP = P - P_old, fock.pyx:24, written straight into a page-locked
+        complex staging buffer) and one copy of the result out of the page-locked output buffer; splitting
+        into real / imaginary planes, the "is the density real" test and re-interleaving G happen on the device."""
         torch = _torch()
         self._install_screen(screen)
         P = np.asarray(P)
         P_old = np.asarray(P_old)
         n = self.Ndev
-        cplx = (np.iscomplexobj(P) or np.iscomplexobj(P_old)) and not np.array_equal(P.imag, P_old.imag)
-        nplane = 2 if cplx else 1
-        pin_in, pin_in_np = self._pinned("dP", (nplane, n, n))
-        pin_out, pin_out_np = self._pinned("G", (nplane, n, n))
-        # dP = P - P_old written straight into the page-locked staging buffer (fock.pyx:24)
+        pin_in, pin_in_np = self._pinned("dP", (n, n), complex)
+        pin_out, pin_out_np = self._pinned("G", (n, n), complex)
         if self.table.identity:
-            np.subtract(P.real, P_old.real, out=pin_in_np[0])
-            if cplx:
-                np.subtract(P.imag, P_old.imag, out=pin_in_np[1])
+            np.subtract(P, P_old, out=pin_in_np)
         else:
-            dPd = self.table.to_dev_matrix(P - P_old)
-            pin_in_np[0] = dPd.real
-            if cplx:
-                pin_in_np[1] = dPd.imag
+            pin_in_np[...] = self.table.to_dev_matrix(P - P_old)
         with torch.cuda.device(self.tdev):
-            dP = pin_in.to(self.tdev, non_blocking=True)
+            d = torch.view_as_real(pin_in.to(self.tdev, non_blocking=True))      # (n, n, 2)
+            dP = d.permute(2, 0, 1).contiguous()                                 # real and imaginary planes
+            cplx = bool(dP[1].any().item())
             G = self._fock_direct_planes(dP, cplx, tol, want_stats, flags)
-            pin_out.copy_(G, non_blocking=True)
+            Gc = torch.complex(G[0], G[1] if cplx else torch.zeros_like(G[0]))
+            pin_out.copy_(Gc, non_blocking=True)
             torch.cuda.current_stream(self.tdev).synchronize()
         self.last_stats = self._last_stats_raw.as_dict() if want_stats else None
-        out = np.empty((n, n), dtype=np.complex128)
-        out.real = pin_out_np[0]
-        out.imag = pin_out_np[1] if cplx else 0.0
-        return self.table.to_user_matrix(out)
+        return self.table.to_user_matrix(pin_out_np.copy())
 
     # ---- device-resident variants for the SCF driver (SURVEY 8f rank 3): no host round trip ------
     @property
