@@ -68,6 +68,9 @@ struct mmdb_basis {
     int nctr = 0;
     cudaStream_t aux_stream = nullptr;            // small class pairs run here, concurrently with the big ones
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t scr_stream = nullptr;            // screening of the NEXT class pair runs here, one task ahead of the ERI kernels
+    cudaEvent_t ev_fork_scr = nullptr;
+    std::vector<cudaEvent_t> ev_pool;             // per-task "list ready" / "list consumed" events of the screening pipeline
     double *scratch_dev = nullptr;
     size_t scratch_cap = 0;   // doubles
 };

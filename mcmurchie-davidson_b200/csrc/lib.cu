@@ -122,6 +122,8 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     cudaFree(b->Dabs_dev); cudaFree(b->DS_dev); cudaFree(b->dglob_dev); cudaFree(b->list_dev);
     cudaFree(b->ctr_dev); cudaFree(b->scratch_dev);
     if (b->aux_stream) { cudaStreamDestroy(b->aux_stream); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
+    if (b->scr_stream) { cudaStreamDestroy(b->scr_stream); cudaEventDestroy(b->ev_fork_scr); }
+    for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
     delete b;
     return MMDB_OK;
 }
@@ -836,8 +838,13 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                 (small ? cap_aux : cap_main) = std::max(small ? cap_aux : cap_main, cap);
             }
         }
-    CHK(ensure_list(b, cap_main + cap_aux));          // [main | aux] regions of one buffer
-    uint2 *list_main = b->list_dev, *list_aux = b->list_dev + cap_main;
+    // Screening pipeline: the main queue's lists are double-buffered and the screen of task m+1 runs on its own
+    // stream while the ERI kernels of task m execute (it fills the SMs the persistent ERI grid vacates at its tail
+    // instead of serialising behind it).  Per-class event timing keeps everything on one stream.
+    const bool pipeline = !timing;
+    CHK(ensure_list(b, (pipeline ? 2 : 1) * cap_main + cap_aux));          // [main 0 | main 1 | aux] regions of one buffer
+    uint2 *list_main[2] = {b->list_dev, b->list_dev + (pipeline ? cap_main : 0)};
+    uint2 *list_aux = b->list_dev + (pipeline ? 2 : 1) * cap_main;
     if ((int)tasks.size() * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
     cudaStream_t sa = st;
     if (cap_aux > 0) {
@@ -850,14 +857,40 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         CU(cudaEventRecord(b->ev_fork, st));           // density screens + zeroed counters are ready
         CU(cudaStreamWaitEvent(sa, b->ev_fork, 0));
     }
+    cudaStream_t ss = st;
+    size_t n_main = 0;
+    for (const Task &t : tasks) n_main += t.aux ? 0 : 1;
+    if (pipeline && n_main > 0) {
+        if (!b->scr_stream) {
+            CU(cudaStreamCreateWithFlags(&b->scr_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&b->ev_fork_scr, cudaEventDisableTiming));
+        }
+        while (b->ev_pool.size() < 2 * n_main) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            b->ev_pool.push_back(e);
+        }
+        ss = b->scr_stream;
+        CU(cudaEventRecord(b->ev_fork_scr, st));       // density screens + zeroed counters are ready
+        CU(cudaStreamWaitEvent(ss, b->ev_fork_scr, 0));
+    }
     int slot = 0;
+    size_t m_main = 0;
     // aux tasks first: they are enqueued (and start) while the host is still launching the big classes
     for (int pass = 0; pass < 2; ++pass)
         for (const Task &t : tasks) {
             if (t.aux != (pass == 0)) continue;
             PairClass &B = b->pc[t.cb], &K = b->pc[t.ck];
             cudaStream_t s1 = t.aux ? sa : st;
-            uint2 *list = t.aux ? list_aux : list_main;
+            const bool piped = pipeline && !t.aux;
+            uint2 *list = t.aux ? list_aux : list_main[piped ? (m_main & 1) : 0];
+            cudaStream_t s_scr = piped ? ss : s1;
+            cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+            if (piped) {
+                ev_ready = b->ev_pool[2 * m_main];
+                ev_done = b->ev_pool[2 * m_main + 1];
+                if (m_main >= 2) CU(cudaStreamWaitEvent(ss, b->ev_pool[2 * (m_main - 2) + 1], 0));   // buffer consumed
+            }
             Launch ln{t.cb, t.ck, slot, nullptr, nullptr, nullptr};
             if (timing) {
                 CU(cudaEventCreate(&ln.e0));
@@ -867,7 +900,11 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             }
             CHK(run_screen(b, B, K, t.cb == t.ck, t.row0, t.row1, shard, nshards, false, tol, slot, true,
                            dP_im_dev != nullptr || (flags & 2) != 0,
-                           (long long)t.cap, list, s1));
+                           (long long)t.cap, list, s_scr));
+            if (piped) {
+                CU(cudaEventRecord(ev_ready, ss));
+                CU(cudaStreamWaitEvent(st, ev_ready, 0));
+            }
             if (timing) CU(cudaEventRecord(ln.em, s1));
             EriArgs a;
             std::memset(&a, 0, sizeof(a));
@@ -880,6 +917,10 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST, 0, s1));
             a.list = list + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + 3;
             CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST_SLOW, 0, s1));
+            if (piped) {
+                CU(cudaEventRecord(ev_done, st));
+                ++m_main;
+            }
             if (timing) CU(cudaEventRecord(ln.e1, s1));
             launches.push_back(ln);
             ++slot;
