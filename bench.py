@@ -33,9 +33,10 @@ SAMPLES = os.path.join(ROOT, "bench_samples")
 # per-function lists), from the ncu --set full capture of the same workload summarised in
 # profiles/r01_ncu_v8_w32_summary.txt.  The traffic is the compact quartet list (8 B/entry) + pair tables; the
 # kernels are FP64-issue bound, not HBM bound.
-NCU_DRAM_BYTES = {"(ss|ss)": 363.6e6, "(ps|ss)": 719.1e6, "(ps|ps)": 344.3e6, "(pp|ss)": 183.0e6, "(pp|ps)": 170.2e6,
-                  "(pp|pp)": 29.9e6, "(ds|ss)": 158.5e6, "(ds|ps)": 151.1e6, "(ds|pp)": 54.3e6, "(ds|ds)": 24.7e6,
-                  "(dp|ss)": 82.9e6, "(dp|ps)": 74.1e6, "(dp|pp)": 31.2e6, "(dp|ds)": 29.3e6}
+NCU_DRAM_BYTES = {"(ss|ss)": 360.3e6, "(ps|ss)": 708.0e6, "(ps|ps)": 345.1e6, "(pp|ss)": 160.2e6, "(pp|ps)": 162.7e6,
+                  "(pp|pp)": 28.1e6, "(ds|ss)": 152.1e6, "(ds|ps)": 148.4e6, "(ds|pp)": 41.1e6, "(ds|ds)": 25.6e6,
+                  "(dp|ss)": 68.3e6, "(dp|ps)": 75.7e6, "(dp|pp)": 26.5e6, "(dp|ds)": 31.1e6, "(dp|dp)": 16.1e6,
+                  "(dd|ss)": 16.9e6, "(dd|ps)": 20.6e6, "(dd|pp)": 9.8e6, "(dd|ds)": 10.8e6, "(dd|dp)": 10.0e6}
 METRIC = "screened_eri_shell_quartets_per_s_direct_fock_build"
 UNIT = "quartets/s"
 
@@ -366,7 +367,7 @@ def main_ours(a):
         ach = fl / (c["ms"] * 1e-3) / 1e12
         roof = {"bound": "fp64_fma", "kernel": "eri_class_kernel %s fused J/K digestion" % name, "achieved": ach, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": NCU_DRAM_BYTES.get(name),
-                "traffic_note": "DRAM bytes of all launches of this class in one build (ncu --set full, profiles/r01_ncu_v8_w32_summary.txt)",
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of all launches of this class in one build (ncu, profiles/r01_ncu_dram_final_w32.csv); = the 8-byte list entries the class consumes",
                 "peak_source": "measured live: DFMA issue probe mmdb_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; nominal 37.2)",
                 "launch_ms": c["ms"], "share_of_step": c["ms"] / sum(x["ms"] + x["screen_ms"] for x in st["classes"].values()),
                 "whole_build": {"model_gflop": mflops / 1e9, "achieved_tflops": mflops / (ms_step * 1e-3) / 1e12,
