@@ -221,24 +221,6 @@ __device__ __forceinline__ void boys_table(double T, const double *__restrict__ 
     }
 }
 
-template <int L>
-__device__ __forceinline__ void boys_eval(double T, const double *__restrict__ tab, double (&F)[L + 1])
-{
-    if (T < (double)boys_tmax_i(L)) {
-        boys_table<L>(T, tab, F);
-    } else {
-        const double rt = fast_rsqrt(T);
-        F[0] = 0.88622692545275801365 * rt;                   // sqrt(pi)/2 / sqrt(T)
-        if constexpr (L > 0) {
-            const double hit = 0.5 * (rt * rt);                // 1/(2T)
-            sfor<0, L>([&](auto I) {
-                constexpr int m = decltype(I)::value;
-                F[m + 1] = ((2 * m + 1) * hit) * F[m];
-            });
-        }
-    }
-}
-
 // runtime-L version for the generic kernel
 __device__ __forceinline__ void boys_eval_rt(int L, double T, const double *__restrict__ tab, double *F)
 {

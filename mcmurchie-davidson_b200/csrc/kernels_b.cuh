@@ -1,7 +1,6 @@
 // kernels_b.cuh — generic (runtime angular momentum) shell-quartet kernel.
-// Used for the classes with L >= 6 ((dp|dp) (dd|pp) (dd|ds) (dd|dp) (dd|dd)), which hold ~1% of the
-// model FLOPs of the target workloads, and as an independent cross-check of the class-specialised
-// kernels (impl = 1).  One thread per (shell quartet, ket component pair); R, E and the Hermite
+// Used for (dd|dd) (a few thousand quartets of the target workloads; minutes of compile time when fully
+// unrolled) and as an independent cross-check of the class-specialised kernels (impl = 1).  One thread per (shell quartet, ket component pair); R, E and the Hermite
 // intermediate are thread-local arrays with runtime indexing.
 #pragma once
 #include "core.cuh"

@@ -448,7 +448,7 @@ __global__ void qs_chunk_max_kernel(const double *Qs, int npairs, double *Qmax)
 
 // Shell-level screen -> compact quartet list.
 // Rows are KET pairs j in [row0,row1) (j % nshards == shard), columns are BRA pairs i (i >= j when the
-// two classes coincide).  One block handles one row x 2048 consecutive columns: 8 candidates per thread,
+// two classes coincide).  One block handles one row x 1024 consecutive columns (two-phase, see the kernel),
 // block-wide prefix sum, ONE atomic per tile to reserve list space.  Entries of a row are written in
 // column order, so consecutive list entries share the ket pair (warp-uniform in the ERI kernels: the
 // inner primitive loop and the J_cd reduction run on broadcast data) and walk the bra pairs.
