@@ -532,3 +532,166 @@ void mdo_onee(long N, long natom, const double *Z, const double *xyz, const doub
     onee_ctx c = {&bs, N, natom, Z, xyz, origin3, S, T, V, M, L};
     parallel_for(N, onee_row, &c);
 }
+
+/* ==============================================================================================
+ * Nuclear-derivative integrals (cython/grad.pyx).  Restated for the NEXT row of the
+ * scope table: the reference differentiates the Hermite coefficient of the differentiated centre,
+ *     Ex(i,j,t) = 2a E(i+1,j,t) - i E(i-1,j,t)                                  (grad.pyx:104-113)
+ * and sums t one order higher; by linearity of the Hermite expansion that is the same as
+ *     d/dA_x [a b|..] = 2a [a+1_x b|..] - l_x [a-1_x b|..]
+ * applied to every primitive with the UNSHIFTED function's norm and coefficient (grad.pyx:74-101),
+ * which is what is coded here (and checked against the reference's own values in tests/).
+ * ============================================================================================== */
+static void shifted(const long *lmn, int x, int delta, long *out)
+{
+    out[0] = lmn[0]; out[1] = lmn[1]; out[2] = lmn[2];
+    out[x] += delta;
+}
+
+/* cython/grad.pyx:74-101 ERIx(a,b,c,d, x, center): centre = 0..3 for 'a'..'d' */
+static double erix_bf(const mdo_basis *bs, const long f[4], int x, int center)
+{
+    double val = 0.0;
+    const double *e[4], *c[4], *n[4];
+    for (int k = 0; k < 4; ++k) {
+        e[k] = bs->exps + bs->off[f[k]];
+        c[k] = bs->coefs + bs->off[f[k]];
+        n[k] = bs->norm + bs->off[f[k]];
+    }
+    long up[3], dn[3];
+    const long *base = bs->shell + 3 * f[center];
+    shifted(base, x, +1, up);
+    shifted(base, x, -1, dn);
+    const long lx = base[x];
+    for (long ja = 0; ja < bs->nprim[f[0]]; ++ja)
+        for (long jb = 0; jb < bs->nprim[f[1]]; ++jb)
+            for (long jc = 0; jc < bs->nprim[f[2]]; ++jc)
+                for (long jd = 0; jd < bs->nprim[f[3]]; ++jd) {
+                    const long j[4] = {ja, jb, jc, jd};
+                    const long *l[4] = {bs->shell + 3 * f[0], bs->shell + 3 * f[1], bs->shell + 3 * f[2], bs->shell + 3 * f[3]};
+                    const double w = n[0][ja] * n[1][jb] * n[2][jc] * n[3][jd] * c[0][ja] * c[1][jb] * c[2][jc] * c[3][jd];
+                    const double alpha = e[center][j[center]];
+                    l[center] = up;
+                    double t = 2.0 * alpha *
+                               mdo_electron_repulsion(e[0][ja], l[0], bs->origin + 3 * f[0], e[1][jb], l[1], bs->origin + 3 * f[1],
+                                                      e[2][jc], l[2], bs->origin + 3 * f[2], e[3][jd], l[3], bs->origin + 3 * f[3]);
+                    if (lx > 0) {
+                        l[center] = dn;
+                        t -= (double)lx *
+                             mdo_electron_repulsion(e[0][ja], l[0], bs->origin + 3 * f[0], e[1][jb], l[1], bs->origin + 3 * f[1],
+                                                    e[2][jc], l[2], bs->origin + 3 * f[2], e[3][jd], l[3], bs->origin + 3 * f[3]);
+                    }
+                    val += w * t;
+                }
+    return val;
+}
+
+/* batched: out[n] = ERIx(idx[4n..4n+3], x = xc[2n], center = xc[2n+1]) */
+typedef struct { const mdo_basis *bs; const long *idx; const long *xc; double *out; } erix_ctx;
+static void erix_body(long q, void *v)
+{
+    erix_ctx *c = (erix_ctx *)v;
+    c->out[q] = erix_bf(c->bs, c->idx + 4 * q, (int)c->xc[2 * q], (int)c->xc[2 * q + 1]);
+}
+void mdo_ERIx_batch(long nbf, const double *origin, const long *shell, const long *nprim, const long *off,
+                    const double *exps, const double *coefs, const double *norm, long n, const long *idx,
+                    const long *xc, double *out)
+{
+    mdo_basis bs = mk(nbf, origin, shell, nprim, off, exps, coefs, norm);
+    erix_ctx c = {&bs, idx, xc, out};
+    parallel_for(n, erix_body, &c);
+}
+
+/* cython/grad.pyx:11-24 Sx and :27-40 Tx (overlapX :352-397, kineticX :400-506): derivative with respect to
+   the centre of a (center = 0) or b (center = 1); kind 0 = overlap, 1 = kinetic energy */
+double mdo_onee_x(long nbf, const double *origin, const long *shell, const long *nprim, const long *off,
+                  const double *exps, const double *coefs, const double *norm, long a, long b, long x, long center,
+                  long kind)
+{
+    mdo_basis bs = mk(nbf, origin, shell, nprim, off, exps, coefs, norm);
+    const long f[2] = {a, b};
+    long up[3], dn[3];
+    const long *base = bs.shell + 3 * f[center];
+    shifted(base, (int)x, +1, up);
+    shifted(base, (int)x, -1, dn);
+    const long lx = base[x];
+    double val = 0.0;
+    for (long ja = 0; ja < bs.nprim[a]; ++ja)
+        for (long jb = 0; jb < bs.nprim[b]; ++jb) {
+            const double ea = bs.exps[bs.off[a] + ja], eb = bs.exps[bs.off[b] + jb];
+            const double w = bs.norm[bs.off[a] + ja] * bs.norm[bs.off[b] + jb] * bs.coefs[bs.off[a] + ja] * bs.coefs[bs.off[b] + jb];
+            const long *l[2] = {bs.shell + 3 * a, bs.shell + 3 * b};
+            const double alpha = center == 0 ? ea : eb;
+            l[center] = up;
+            double t = 2.0 * alpha * (kind == 0 ? p_overlap(ea, l[0], bs.origin + 3 * a, eb, l[1], bs.origin + 3 * b)
+                                                : p_kinetic(ea, l[0], bs.origin + 3 * a, eb, l[1], bs.origin + 3 * b));
+            if (lx > 0) {
+                l[center] = dn;
+                t -= (double)lx * (kind == 0 ? p_overlap(ea, l[0], bs.origin + 3 * a, eb, l[1], bs.origin + 3 * b)
+                                             : p_kinetic(ea, l[0], bs.origin + 3 * a, eb, l[1], bs.origin + 3 * b));
+            }
+            val += w * t;
+        }
+    return val;
+}
+
+/* cython/grad.pyx:509-550 nuclear_attractionXa: derivative of the OPERATOR 1/|r - C| with respect to C_x
+   (Hellmann-Feynman term): -sum E E E R_{t+1_x,u,v} * 2 pi / p */
+static double p_nuclear_dC(double a, const long *l1, const double *A, double b, const long *l2, const double *B,
+                           const double *C, int x)
+{
+    double p = a + b;
+    double P[3];
+    for (int d = 0; d < 3; ++d) P[d] = (a * A[d] + b * B[d]) / p;
+    double RPC = sqrt((P[0] - C[0]) * (P[0] - C[0]) + (P[1] - C[1]) * (P[1] - C[1]) + (P[2] - C[2]) * (P[2] - C[2]));
+    double leaf[MDO_MAXN];
+    int L = (int)(l1[0] + l1[1] + l1[2] + l2[0] + l2[1] + l2[2]) + 1;
+    R_leaves(L, p, RPC, leaf);
+    double val = 0.0;
+    for (int t = 0; t <= l1[0] + l2[0]; ++t)
+        for (int u = 0; u <= l1[1] + l2[1]; ++u)
+            for (int v = 0; v <= l1[2] + l2[2]; ++v)
+                val -= mdo_E(l1[0], l2[0], t, A[0] - B[0], a, b) * mdo_E(l1[1], l2[1], u, A[1] - B[1], a, b) *
+                       mdo_E(l1[2], l2[2], v, A[2] - B[2], a, b) *
+                       R_rec(t + (x == 0), u + (x == 1), v + (x == 2), 0, leaf, P[0] - C[0], P[1] - C[1], P[2] - C[2]);
+    return val * 2 * MDO_PI / p;
+}
+
+/* cython/grad.pyx:43-71 VxA (mode 2: operator derivative) and VxB (mode 0 / 1: derivative with respect to the
+   centre of a / b, grad.pyx:553-629) for the nucleus at C */
+double mdo_V_x(long nbf, const double *origin, const long *shell, const long *nprim, const long *off,
+               const double *exps, const double *coefs, const double *norm, long a, long b, const double *C, long x,
+               long mode)
+{
+    mdo_basis bs = mk(nbf, origin, shell, nprim, off, exps, coefs, norm);
+    const long f[2] = {a, b};
+    double val = 0.0;
+    long up[3], dn[3];
+    long lx = 0;
+    if (mode < 2) {
+        const long *base = bs.shell + 3 * f[mode];
+        shifted(base, (int)x, +1, up);
+        shifted(base, (int)x, -1, dn);
+        lx = base[x];
+    }
+    for (long ja = 0; ja < bs.nprim[a]; ++ja)
+        for (long jb = 0; jb < bs.nprim[b]; ++jb) {
+            const double ea = bs.exps[bs.off[a] + ja], eb = bs.exps[bs.off[b] + jb];
+            const double w = bs.norm[bs.off[a] + ja] * bs.norm[bs.off[b] + jb] * bs.coefs[bs.off[a] + ja] * bs.coefs[bs.off[b] + jb];
+            const long *l[2] = {bs.shell + 3 * a, bs.shell + 3 * b};
+            double t;
+            if (mode == 2) {
+                t = p_nuclear_dC(ea, l[0], bs.origin + 3 * a, eb, l[1], bs.origin + 3 * b, C, (int)x);
+            } else {
+                const double alpha = mode == 0 ? ea : eb;
+                l[mode] = up;
+                t = 2.0 * alpha * p_nuclear(ea, l[0], bs.origin + 3 * a, eb, l[1], bs.origin + 3 * b, C);
+                if (lx > 0) {
+                    l[mode] = dn;
+                    t -= (double)lx * p_nuclear(ea, l[0], bs.origin + 3 * a, eb, l[1], bs.origin + 3 * b, C);
+                }
+            }
+            val += w * t;
+        }
+    return val;
+}

@@ -54,6 +54,12 @@ def lib():
         L.mdo_onee.argtypes = [C.c_long, C.c_long, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp] + basis
         L.mdo_jk_incore.restype = None
         L.mdo_jk_incore.argtypes = [C.c_long, _dp, _dp, _dp, _dp]
+        L.mdo_ERIx_batch.restype = None
+        L.mdo_ERIx_batch.argtypes = [C.c_long] + basis + [C.c_long, _lp, _lp, _dp]
+        L.mdo_onee_x.restype = C.c_double
+        L.mdo_onee_x.argtypes = [C.c_long] + basis + [C.c_long] * 5
+        L.mdo_V_x.restype = C.c_double
+        L.mdo_V_x.argtypes = [C.c_long] + basis + [C.c_long, C.c_long, _dp, C.c_long, C.c_long]
         _LIB = L
     return _LIB
 
@@ -170,3 +176,45 @@ def onee(bfs, charges, coords, origin):
     M = np.zeros((3, N, N)); Lm = np.zeros((3, N, N))
     lib().mdo_onee(N, len(Z), Z, xyz, org, S.reshape(-1), T.reshape(-1), V.reshape(-1), M.reshape(-1), Lm.reshape(-1), *fb.args())
     return S, T, V, M, Lm
+
+
+# ---- nuclear-derivative integrals (cython/grad.pyx; the next row of the scope table) ------------
+_CENTER = {"a": 0, "b": 1, "c": 2, "d": 3}
+
+
+def ERIx_batch(bfs, idx, x, center):
+    """d/dX of (ij|kl) for idx[n,4]; x[n] in 0..2, center[n] in 0..3 (or 'a'..'d'): grad.pyx:74-101."""
+    fb = _fb(bfs)
+    idx = np.ascontiguousarray(idx, dtype=np.int64).reshape(-1, 4)
+    cen = [(_CENTER[c.lower()] if isinstance(c, str) else int(c)) for c in np.atleast_1d(center)]
+    xc = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(x, dtype=np.int64), len(idx)),
+                                        np.broadcast_to(np.asarray(cen, dtype=np.int64), len(idx))], axis=1)).reshape(-1)
+    out = np.zeros(len(idx))
+    lib().mdo_ERIx_batch(fb.nbf, *fb.args(), len(idx), idx.reshape(-1), xc, out)
+    return out
+
+
+def ERIx(a, b, c, d, x=0, center="a"):
+    return float(ERIx_batch([a, b, c, d], [[0, 1, 2, 3]], [x], [center])[0])
+
+
+def Sx(a, b, x=0, center="A"):
+    fb = FlatBasis([a, b])
+    return lib().mdo_onee_x(2, *fb.args(), 0, 1, int(x), 0 if center.upper() == "A" else 1, 0)
+
+
+def Tx(a, b, x=0, center="A"):
+    fb = FlatBasis([a, b])
+    return lib().mdo_onee_x(2, *fb.args(), 0, 1, int(x), 0 if center.upper() == "A" else 1, 1)
+
+
+def VxA(a, b, C, x=0):
+    """Operator (Hellmann-Feynman) derivative of the nuclear attraction integral: grad.pyx:43-54."""
+    fb = FlatBasis([a, b])
+    return lib().mdo_V_x(2, *fb.args(), 0, 1, np.ascontiguousarray(C, dtype=np.float64), int(x), 2)
+
+
+def VxB(a, b, C, x=0, center="A"):
+    """Basis-function-centre derivative of the nuclear attraction integral: grad.pyx:59-71."""
+    fb = FlatBasis([a, b])
+    return lib().mdo_V_x(2, *fb.args(), 0, 1, np.ascontiguousarray(C, dtype=np.float64), int(x), 0 if center.upper() == "A" else 1)

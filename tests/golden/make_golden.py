@@ -15,6 +15,9 @@ Fixtures
     sampled_<config>.npz    random basis-function quartets of the benchmark configurations with the
                             reference's ERI values (stratified over angular-momentum classes)
     boys_kat.json           the Boys known-answer table of the reference's tests/test012.py
+    grad_h2o.npz            nuclear-derivative integrals of the reference's cython/grad.pyx (ERIx, Sx, Tx, VxA,
+                            VxB) on random function tuples of H2O/STO-3G and H2O/cc-pVDZ — pins the oracle's
+                            restatement of the NEXT scope row; `--grad-only` writes just this
 """
 import importlib.util
 import io
@@ -208,8 +211,40 @@ def boys_kat():
     print("boys KATs:", len(kats))
 
 
+def grad_fixture():
+    """Derivative integrals straight from the reference's compiled grad module."""
+    from mmd.integrals import grad as G
+    out = {}
+    for tag, basis in (("sto3g", "sto-3g"), ("ccpvdz", "cc-pvdz")):
+        mol = Molecule(geometry=synth.water(), basis=basis)
+        bfs, N = mol.bfs, mol.nbasis
+        rng = np.random.default_rng(7)
+        n4, n2 = (200, 150) if tag == "sto3g" else (300, 200)
+        idx = rng.integers(0, N, size=(n4, 4))
+        xs, cs = rng.integers(0, 3, size=n4), rng.integers(0, 4, size=n4)
+        out[tag + "_eri_idx"], out[tag + "_eri_x"], out[tag + "_eri_c"] = idx, xs, cs
+        out[tag + "_eri"] = np.array([G.ERIx(bfs[i], bfs[j], bfs[k], bfs[l], x=int(x), center="abcd"[c])
+                                      for (i, j, k, l), x, c in zip(idx, xs, cs)])
+        pr = rng.integers(0, N, size=(n2, 2))
+        x2, c2, at = rng.integers(0, 3, size=n2), rng.integers(0, 2, size=n2), rng.integers(0, len(mol.atoms), size=n2)
+        out[tag + "_pr"], out[tag + "_x2"], out[tag + "_c2"], out[tag + "_atom"] = pr, x2, c2, at
+        out[tag + "_atoms_xyz"] = np.array([a.origin for a in mol.atoms])
+        out[tag + "_S"] = np.array([G.Sx(bfs[i], bfs[j], x=int(x), center="AB"[c]) for (i, j), x, c in zip(pr, x2, c2)])
+        out[tag + "_T"] = np.array([G.Tx(bfs[i], bfs[j], x=int(x), center="AB"[c]) for (i, j), x, c in zip(pr, x2, c2)])
+        out[tag + "_VA"] = np.array([G.VxA(bfs[i], bfs[j], np.asarray(mol.atoms[a].origin), x=int(x))
+                                     for (i, j), x, a in zip(pr, x2, at)])
+        out[tag + "_VB"] = np.array([G.VxB(bfs[i], bfs[j], np.asarray(mol.atoms[a].origin), x=int(x), center="AB"[c])
+                                     for (i, j), x, c, a in zip(pr, x2, c2, at)])
+    np.savez_compressed(os.path.join(HERE, "grad_h2o.npz"), **out)
+    print("grad fixture:", {k: v.shape for k, v in out.items() if k.endswith(("_eri", "_S"))})
+
+
 def main():
+    if "--grad-only" in sys.argv:
+        grad_fixture()
+        return
     boys_kat()
+    grad_fixture()
     anchors = {}
     anchors["h2o_sto3g_incore"] = small_molecule_fixture("h2o_sto3g", synth.water(), "sto-3g", pack=False)
     anchors["h2o_ccpvdz_incore"] = small_molecule_fixture("h2o_ccpvdz", synth.water(), "cc-pvdz", pack=True)
