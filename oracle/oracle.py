@@ -218,3 +218,61 @@ def VxB(a, b, C, x=0, center="A"):
     """Basis-function-centre derivative of the nuclear attraction integral: grad.pyx:59-71."""
     fb = FlatBasis([a, b])
     return lib().mdo_V_x(2, *fb.args(), 0, 1, np.ascontiguousarray(C, dtype=np.float64), int(x), 0 if center.upper() == "A" else 1)
+
+
+def forces(bfs, charges, coords, masks, P, F):
+    """RHF nuclear forces -dE/dX (natom, 3) by the reference's recipe (mmd/forces.py:8-99): derivative one-electron
+    matrices, the derivative two-electron tensor with its 8-fold symmetry, 2J-K contraction, energy-weighted
+    density for the overlap term and the nuclear repulsion.  NumPy + the C derivative integrals above; the N^4
+    tensor per atom and direction makes it a small-molecule checker (as in the reference)."""
+    bfs = list(bfs)
+    N = len(bfs)
+    Z = np.asarray(charges, dtype=np.float64)
+    xyz = np.asarray(coords, dtype=np.float64).reshape(-1, 3)
+    masks = np.asarray(masks, dtype=np.float64).reshape(len(Z), N)
+    P = np.asarray(P)
+    F = np.asarray(F)
+    fb = FlatBasis(bfs)
+    # canonical quartets i>=j, k>=l, ij>=kl (forces.py:61-67)
+    i2, j2 = np.tril_indices(N)
+    ij = i2 * (i2 + 1) // 2 + j2
+    A, B = np.meshgrid(np.arange(len(ij)), np.arange(len(ij)), indexing="ij")
+    keep = ij[A] >= ij[B]
+    quart = np.stack([i2[A[keep]], j2[A[keep]], i2[B[keep]], j2[B[keep]]], axis=1)
+    W = P @ F @ P
+    out = np.zeros((len(Z), 3))
+    for a in range(len(Z)):
+        m = masks[a]
+        for x in range(3):
+            dS = np.zeros((N, N)); dT = np.zeros((N, N)); dV = np.zeros((N, N))
+            for i in range(N):
+                for j in range(i + 1):
+                    dS[i, j] = dS[j, i] = m[i] * Sx(bfs[i], bfs[j], x, "A") + m[j] * Sx(bfs[i], bfs[j], x, "B")
+                    dT[i, j] = dT[j, i] = m[i] * Tx(bfs[i], bfs[j], x, "A") + m[j] * Tx(bfs[i], bfs[j], x, "B")
+                    v = -Z[a] * VxA(bfs[i], bfs[j], xyz[a], x)
+                    for c in range(len(Z)):
+                        v -= m[i] * Z[c] * VxB(bfs[i], bfs[j], xyz[c], x, "A")
+                        v -= m[j] * Z[c] * VxB(bfs[i], bfs[j], xyz[c], x, "B")
+                    dV[i, j] = dV[j, i] = v
+            dVN = 0.0
+            for c in range(len(Z)):
+                R = np.linalg.norm(xyz[a] - xyz[c])
+                if not np.allclose(R, 0.0):
+                    dVN += -(xyz[a, x] - xyz[c, x]) * Z[a] * Z[c] / R ** 3
+            val = np.zeros(len(quart))
+            for cen in range(4):
+                w = m[quart[:, cen]]
+                sel = np.nonzero(w)[0]
+                if len(sel):
+                    val[sel] += w[sel] * ERIx_batch(fb, quart[sel], np.full(len(sel), x), np.full(len(sel), cen))
+            dG = np.zeros((N, N, N, N))
+            i, j, k, l = quart.T
+            for p_ in ((i, j, k, l), (k, l, i, j), (j, i, l, k), (l, k, j, i), (j, i, k, l), (l, k, i, j), (i, j, l, k), (k, l, j, i)):
+                dG[p_] = val
+            Hx = dT + dV
+            Jx = np.einsum("pqrs,sr->pq", dG, P)
+            Kx = np.einsum("psqr,sr->pq", dG, P)
+            Fx = Hx + 2.0 * Jx - Kx
+            force = np.einsum("pq,qp", P, Fx + Hx) - 2.0 * np.einsum("pq,qp", dS, W) + dVN
+            out[a, x] = np.real(-force)
+    return out

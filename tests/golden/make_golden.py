@@ -235,6 +235,14 @@ def grad_fixture():
                                      for (i, j), x, a in zip(pr, x2, at)])
         out[tag + "_VB"] = np.array([G.VxB(bfs[i], bfs[j], np.asarray(mol.atoms[a].origin), x=int(x), center="AB"[c])
                                      for (i, j), x, c, a in zip(pr, x2, c2, at)])
+    # RHF forces of the reference (mmd/forces.py) with the converged P and F they were computed from
+    h2 = "\n0 1\nH 0.0 0.0 0.74\nH 0.0 0.0 0.0\n"
+    for tag, geom in (("h2", h2), ("h2o", synth.water())):
+        mol = Molecule(geometry=geom, basis="sto-3g")
+        quiet(mol.RHF)
+        quiet(mol.forces)
+        out["forces_" + tag] = np.array([a.forces for a in mol.atoms])
+        out["forces_" + tag + "_P"], out["forces_" + tag + "_F"] = np.asarray(mol.P), np.asarray(mol.F)
     np.savez_compressed(os.path.join(HERE, "grad_h2o.npz"), **out)
     print("grad fixture:", {k: v.shape for k, v in out.items() if k.endswith(("_eri", "_S"))})
 
