@@ -134,6 +134,13 @@ class Molecule(SCF):
         self.TwoE = np.zeros((N, N, N, N))
         self.TwoE = np.asarray(doERIs(N, self.TwoE, self.bfs))
 
+    def forces(self):
+        """Nuclear gradient (mmd/forces.py of the reference).  Not part of the accelerated path yet: the device
+        side of the derivative integrals is not built, and this package has no CPU fallback
+        by design — fail loudly instead of returning slow or approximate forces."""
+        raise NotImplementedError("Molecule.forces(): derivative ERIs / gradient J/K are not built on the B200 path yet "
+                                  "(see DESIGN.md section 8); the CPU oracle (oracle.forces) is test infrastructure only")
+
     def save_integrals(self, folder=None):
         """Crawford-format text dump (enuc, nbf, nelec, s, t, v, eri with 1-based indices)."""
         if folder is None:

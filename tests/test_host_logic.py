@@ -200,6 +200,14 @@ def test_device_resident_scf_loop_matches_host_loop(monkeypatch, direct):
     assert np.abs(np.asarray(dev.mu) - np.asarray(host.mu)).max() < 1e-7
 
 
+def test_forces_fail_loudly_until_the_gradient_path_exists():
+    from mmd._b200 import synth
+    from mmd.molecule import Molecule
+    mol = Molecule(synth.water(), "sto-3g")
+    with pytest.raises(NotImplementedError):
+        mol.forces()
+
+
 def test_printed_summary_format(monkeypatch, capsys):
     oracle_engine.install(monkeypatch)
     from mmd.molecule import Molecule
