@@ -220,7 +220,7 @@ def VxB(a, b, C, x=0, center="A"):
     return lib().mdo_V_x(2, *fb.args(), 0, 1, np.ascontiguousarray(C, dtype=np.float64), int(x), 0 if center.upper() == "A" else 1)
 
 
-def forces(bfs, charges, coords, masks, P, F):
+def forces(bfs, charges, coords, masks, P, F, only=None):
     """RHF nuclear forces -dE/dX (natom, 3) by the reference's recipe (mmd/forces.py:8-99): derivative one-electron
     matrices, the derivative two-electron tensor with its 8-fold symmetry, 2J-K contraction, energy-weighted
     density for the overlap term and the nuclear repulsion.  NumPy + the C derivative integrals above; the N^4
@@ -244,6 +244,8 @@ def forces(bfs, charges, coords, masks, P, F):
     for a in range(len(Z)):
         m = masks[a]
         for x in range(3):
+            if only is not None and (a, x) not in only:      # restrict to some (atom, direction) components
+                continue
             dS = np.zeros((N, N)); dT = np.zeros((N, N)); dV = np.zeros((N, N))
             for i in range(N):
                 for j in range(i + 1):

@@ -237,8 +237,8 @@ def grad_fixture():
                                      for (i, j), x, c, a in zip(pr, x2, c2, at)])
     # RHF forces of the reference (mmd/forces.py) with the converged P and F they were computed from
     h2 = "\n0 1\nH 0.0 0.0 0.74\nH 0.0 0.0 0.0\n"
-    for tag, geom in (("h2", h2), ("h2o", synth.water())):
-        mol = Molecule(geometry=geom, basis="sto-3g")
+    for tag, geom, basis in (("h2", h2, "sto-3g"), ("h2o", synth.water(), "sto-3g"), ("h2o_ccpvdz", synth.water(), "cc-pvdz")):
+        mol = Molecule(geometry=geom, basis=basis)      # cc-pVDZ: d functions -> f-type shifted integrals (minutes in the reference)
         quiet(mol.RHF)
         quiet(mol.forces)
         out["forces_" + tag] = np.array([a.forces for a in mol.atoms])
