@@ -118,7 +118,11 @@ typedef struct {
  * flags: bit0 = time each class launch with CUDA events (fills stats->class_ms; synchronises);
  *        bit1 = DETERMINISTIC accumulation: contributions are rounded to multiples of 2^-50 and added with 64-bit
  *               integer atomics, so G is bitwise reproducible for any schedule / shard count.  G then holds scaled
- *               integers: sum the shards as int64 and finish with mmdb_fixed_to_double. */
+ *               integers: sum the shards as int64 and finish with mmdb_fixed_to_double.
+ * Streams: the call is asynchronous with respect to the host and ordered on `stream` — everything enqueued on
+ * `stream` after it sees the complete G.  Internally it forks onto two handle-owned streams (small class pairs;
+ * the screening pipeline that runs one class pair ahead of the ERI kernels) and joins them back with events,
+ * so ONE build per handle may be in flight at a time.  With `stats` (or flags bit0) the call synchronises. */
 int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const double *dP_im_dev, double tol,
                      double *G_re_dev, double *G_im_dev, int shard, int nshards, int flags,
                      mmdb_fock_stats *stats, void *stream);
