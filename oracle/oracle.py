@@ -278,3 +278,31 @@ def forces(bfs, charges, coords, masks, P, F, only=None):
             force = np.einsum("pq,qp", P, Fx + Hx) - 2.0 * np.einsum("pq,qp", dS, W) + dVN
             out[a, x] = np.real(-force)
     return out
+
+
+def forces_2e_contracted(bfs, masks, P):
+    """Two-electron part of dE/dX (natom, 3) WITHOUT the N^4 derivative tensor of mmd/forces.py:61-92: every canonical
+    quartet i>=j, k>=l, ij>=kl contributes
+        (deg / 8) * [16 P_ij P_kl - 4 P_ik P_jl - 4 P_il P_jk] * sum_{centres c on the atom} d(ij|kl)/dX_c
+    with the degeneracy of cython/fock.pyx:60-70.  It equals einsum(P, 2 Jx - Kx) of the reference for a real
+    symmetric P (P = C_occ C_occ^T, no factor 2) — the contraction a device gradient kernel performs as it goes
+    (SURVEY 8f rank 4); tests/test_oracle_pinned.py checks it against the tensor route."""
+    bfs = list(bfs)
+    N = len(bfs)
+    masks = np.asarray(masks, dtype=np.float64).reshape(-1, N)
+    P = np.real(np.asarray(P))
+    fb = FlatBasis(bfs)
+    i2, j2 = np.tril_indices(N)
+    ij = i2 * (i2 + 1) // 2 + j2
+    A, B = np.meshgrid(np.arange(len(ij)), np.arange(len(ij)), indexing="ij")
+    keep = ij[A] >= ij[B]
+    q = np.stack([i2[A[keep]], j2[A[keep]], i2[B[keep]], j2[B[keep]]], axis=1)
+    i, j, k, l = q.T
+    deg = np.where(i == j, 1.0, 2.0) * np.where(k == l, 1.0, 2.0) * np.where((i == k) & (j == l), 1.0, 2.0)
+    w = deg / 8.0 * (16.0 * P[i, j] * P[k, l] - 4.0 * P[i, k] * P[j, l] - 4.0 * P[i, l] * P[j, k])
+    out = np.zeros((len(masks), 3))
+    for x in range(3):
+        for cen in range(4):
+            d = ERIx_batch(fb, q, np.full(len(q), x), np.full(len(q), cen))
+            out[:, x] += masks[:, q[:, cen]] @ (w * d)
+    return out
