@@ -230,3 +230,25 @@ def test_geometry_units_and_center_of_charge():
     z = np.array([8, 1, 1.0])
     xyz = np.array([a.origin for a in mol.atoms])
     assert np.allclose(mol.center_of_charge, (z[:, None] * xyz).sum(0) / z.sum(), atol=1e-15)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: one JSON line with the contract's keys, timed on the host with oracle/_ref (or
+    the oracle port), no GPU involved."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference"
+    if "unavailable" in line:
+        return
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["metric"] == "screened_eri_shell_quartets_per_s_direct_fock_build" and line["unit"] == "quartets/s"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
