@@ -81,6 +81,20 @@ def test_sampled_quartets_benchmark_configs(golden, cfg):
     assert np.abs(got - g["schwarz_vals"]).max() < ERI_TOL
 
 
+@pytest.mark.parametrize("cfg", ["benzene_631gss", "w8_ccpvdz", "c20h42_631gs", "w32_ccpvdz"])
+def test_big_stratified_samples_benchmark_configs(golden, cfg):
+    """The reference's own ERI values on >= 1e4 function quartets per class (2.5e3 for configurations 2 and 3), five
+    pair-distance bins per class: elementwise <= 1e-12 for the class kernels AND the generic kernel."""
+    g = golden("sampled_big_%s.npz" % cfg)
+    mol = Molecule(*synth.config(cfg))
+    eng = mol.engine
+    idx = g["idx"].astype(np.int64)
+    err = np.abs(eng.eri_quartets(idx) - g["vals"])
+    assert err.max() < ERI_TOL, (int(err.argmax()), idx[err.argmax()], float(err.max()))
+    sub = slice(0, None, 7)
+    assert np.abs(eng.eri_quartets(idx[sub], impl=1) - g["vals"][sub]).max() < ERI_TOL
+
+
 @pytest.mark.parametrize("cfg", ["h2o_sto3g", "h2o_ccpvdz"])
 def test_schwarz_formPT_jk_onee(oracle, golden, cfg):
     g = golden(cfg + ".npz")
@@ -321,6 +335,42 @@ def test_direct_build_equals_incore_build(cfg):
     G12 = eng.formPT(P, np.zeros_like(P), screen=scr, tol=1e-12)
     assert np.abs(0.5 * (G12 + G12.T) - G).max() < 1e-9
     del T
+
+
+def closed_form_densities(bfs):
+    """The two closed-form densities of tests/golden/make_golden_fock.py (bit-reproducible from the geometry)."""
+    N = len(bfs)
+    C = np.array([np.asarray(b.origin, dtype=np.float64) for b in bfs])
+    i = np.arange(N, dtype=np.float64)
+    A = 0.1 * np.cos(0.37 * (i[:, None] + i[None, :])) + 0.05 * np.cos(0.011 * (i[:, None] - i[None, :]) ** 2)
+    A = 0.5 * (A + A.T)
+    r2 = ((C[:, None, :] - C[None, :, :]) ** 2).sum(-1)
+    B = np.exp(-0.35 * r2) * (0.3 * np.cos(0.61 * (i[:, None] + i[None, :])) + 0.2)
+    B = 0.5 * (B + B.T)
+    return {"A": A, "B": B}
+
+
+@pytest.mark.parametrize("cfg", ["c20h42_631gs", "w32_ccpvdz"])
+def test_benchmark_size_fock_elements_vs_oracle(golden, cfg):
+    """Configurations 4 and 5 against the ORACLE (not against another GPU path): 43-48 stratified elements of
+    sym(G) = 2J - K, each summed integral by integral (1e5-4e5 ERIs per element) by the pinned C oracle
+    (tests/golden/make_golden_fock.py), for a dense and a local closed-form density.  Row chunking of the lists,
+    the auxiliary stream, the screening pipeline and the bra slices only engage at these sizes; a chunk that was
+    dropped consistently would show here.  tol = 0 (no screening) and the production tol = 1e-12."""
+    g = golden("fock_elements_%s.npz" % cfg)
+    mol = Molecule(*synth.config(cfg))
+    assert mol.nbasis == int(g["nbasis"])
+    eng = mol.engine
+    scr = eng.schwarz()
+    el = g["elements"]
+    for name, P in closed_form_densities(mol.bfs).items():
+        Pc = P.astype(complex)
+        for tol in (0.0, 1e-12):
+            G = eng.formPT(Pc, np.zeros_like(Pc), screen=scr, tol=tol)
+            assert np.abs(G.imag).max() == 0.0
+            Gs = 0.5 * (G.real + G.real.T)
+            err = np.abs(Gs[el[:, 0], el[:, 1]] - g["G_" + name])
+            assert err.max() < FOCK_TOL, (cfg, name, tol, el[err.argmax()], float(err.max()))
 
 
 def test_full_size_direct_build_properties():
