@@ -153,6 +153,10 @@ int mmdb_ao2mo_mp2(int device, const double *TwoE_dev, int N, int nocc, const do
 /* ---- utilities --------------------------------------------------------------------------- */
 /* F_0..F_mmax(T[i]) evaluated on the device with the kernels' Boys routine: out[i*(mmax+1)+m]. */
 int mmdb_boys_host(int device, int mmax, int64_t n, const double *T, double *out);
+/* The same through the class kernels' TEMPLATED routine for total angular momentum L (0..8): Taylor table below the
+ * class's own switch-over T_max(L) = 37,41,44,47,50,53,55,58,60, alpha-free asymptotic series at and above it
+ * (csrc/core.cuh prim_Fs<L>).  out[i*(L+1)+m] = F_m(T[i]). */
+int mmdb_boys_class_host(int device, int L, int64_t n, const double *T, double *out);
 /* Peak FP64 FMA issue rate probe: runs a register-resident DFMA loop, returns TFLOP/s. */
 int mmdb_fp64_peak(int device, double *tflops, float *ms);
 /* FLOP model of SURVEY §8(d): flops per primitive shell quartet of class (la lb|lc ld). */

@@ -358,14 +358,14 @@ __device__ __forceinline__ void build_R_impl(RS &R, const double (&Fs)[L + 1], d
 // i.e. ONE reciprocal square root (of |PQ|^2) and a product chain; the branch is taken on
 // p q |PQ|^2 >= T_max (p+q), which needs no division either.  The table branch pays one extra rsqrt
 // (sqrt(alpha)) to undo the normalisation.
-template <int L, class RS>
-__device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, double cck, double X, double Y, double Z,
-                                       const double *__restrict__ boys_tab)
+// Fs[n] = s (-2 alpha)^n F_n(alpha |PQ|^2), the seeds of the R recursion, for one primitive quartet (both Boys
+// branches; this is the routine mmdb_boys_class_host probes, per L, across its own T_max(L) switch)
+template <int L>
+__device__ __forceinline__ void prim_Fs(double (&Fs)[L + 1], double pb, double pk, double ccb, double cck, double R2,
+                                        const double *__restrict__ boys_tab)
 {
-    const double R2 = X * X + Y * Y + Z * Z;
     const double pp = pb * pk, ps = pb + pk;
     const double c2 = ccb * cck;
-    double Fs[L + 1];
     if (pp * R2 >= (double)boys_tmax_i(L) * ps) {
         const double ri = fast_rsqrt(R2);
         Fs[0] = (0.88622692545275801365 * c2) * ri;
@@ -385,6 +385,15 @@ __device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, 
 #pragma unroll
         for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
     }
+}
+
+template <int L, class RS>
+__device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, double cck, double X, double Y, double Z,
+                                       const double *__restrict__ boys_tab)
+{
+    const double R2 = X * X + Y * Y + Z * Z;
+    double Fs[L + 1];
+    prim_Fs<L>(Fs, pb, pk, ccb, cck, R2, boys_tab);
     build_R_impl<L>(R, Fs, X, Y, Z);
 }
 

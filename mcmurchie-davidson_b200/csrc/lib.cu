@@ -1135,6 +1135,48 @@ extern "C" int mmdb_boys_host(int device, int mmax, int64_t n, const double *T, 
     return MMDB_OK;
 }
 
+// Probe of the TEMPLATED Boys path the class kernels run (prim_Fs<L>: boys_table<L> below T_max(L), the alpha-free
+// asymptotic branch at and above it).  With p = q = 2 (alpha = 1) and unit pair coefficients, T = |PQ|^2 and
+// Fs[n] = (-2)^n F_n(T).
+template <int L>
+__global__ void boys_class_probe_kernel(int64_t n, const double *T, const double *tab, double *out)
+{
+    extern __shared__ double s_boys[];
+    for (int x = threadIdx.x; x < boys_rows(L) * BOYS_STRIDE; x += blockDim.x) s_boys[x] = tab[x];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double Fs[L + 1];
+        prim_Fs<L>(Fs, 2.0, 2.0, 1.0, 1.0, T[i], s_boys);
+        double sc = 1.0;
+#pragma unroll
+        for (int m = 0; m <= L; ++m) { out[i * (L + 1) + m] = Fs[m] * sc; sc *= -0.5; }
+    }
+}
+
+extern "C" int mmdb_boys_class_host(int device, int L, int64_t n, const double *T, double *out)
+{
+    if (L < 0 || L > BOYS_MAXL) return fail(MMDB_ERR_INVALID, "mmdb_boys_class_host: L out of range");
+    CU(cudaSetDevice(device));
+    std::vector<double> tab;
+    make_boys_table(L, tab);
+    double *dtab = nullptr, *dT = nullptr, *dout = nullptr;
+    CU(cudaMalloc(&dtab, tab.size() * sizeof(double)));
+    CU(cudaMalloc(&dT, n * sizeof(double)));
+    CU(cudaMalloc(&dout, n * (L + 1) * sizeof(double)));
+    CU(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dT, T, n * sizeof(double), cudaMemcpyHostToDevice));
+    const size_t smem = (size_t)BOYS_ROWS * BOYS_STRIDE * sizeof(double);
+    switch (L) {
+#define PROBE(LL) case LL: boys_class_probe_kernel<LL><<<148, 128, smem>>>(n, dT, dtab, dout); break;
+        PROBE(0) PROBE(1) PROBE(2) PROBE(3) PROBE(4) PROBE(5) PROBE(6) PROBE(7) PROBE(8)
+#undef PROBE
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout, n * (L + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dtab); cudaFree(dT); cudaFree(dout);
+    return MMDB_OK;
+}
+
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double c)
 {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -392,6 +392,17 @@ def boys(n, T):
     return out
 
 
+def boys_class(L_tot, T):
+    """F_0..F_L(T) through the class kernels' templated Boys routine for total angular momentum L_tot
+    (its own table/asymptotic switch-over T_max(L)); test hook."""
+    L.require_gpu()
+    Ts = np.ascontiguousarray(np.atleast_1d(np.asarray(T, dtype=np.float64)))
+    n = int(L_tot)
+    out = np.zeros((len(Ts), n + 1))
+    L.check(L.load().mmdb_boys_class_host(_torch().cuda.current_device(), n, len(Ts), L.ptr(Ts), L.ptr(out)))
+    return out
+
+
 def fp64_peak(device=0):
     L.require_gpu()
     tf = C.c_double(0.0)

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mmdb_onee_host": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmdb_ao2mo_mp2": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _dp, _vp]),
     "mmdb_boys_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp]),
+    "mmdb_boys_class_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp]),
     "mmdb_fp64_peak": (C.c_int, [C.c_int, _dp, C.POINTER(C.c_float)]),
     "mmdb_class_flops": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int]),
 }
