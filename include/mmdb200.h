@@ -114,7 +114,8 @@ typedef struct {
  * UN-symmetrised matrix.  dP = P - P_old is formed by the caller.  mmdb_schwarz must have been
  * called on the handle.  G planes must be zeroed by the caller (the call accumulates), which lets
  * shards of one build add into one buffer.  Work is restricted to shard `shard` of `nshards`
- * (static cost-balanced split of bra shell pairs); nshards = 1 does the whole build.
+ * (static cost-balanced split: ket-pair row j of every class pair belongs to shard j % nshards); nshards = 1 does the
+ * whole build.
  * flags: bit0 = time each class launch with CUDA events (fills stats->class_ms; synchronises);
  *        bit1 = DETERMINISTIC accumulation: contributions are rounded to multiples of 2^-50 and added with 64-bit
  *               integer atomics, so G is bitwise reproducible for any schedule / shard count.  G then holds scaled
@@ -129,11 +130,29 @@ int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const double *dP_im
 
 int mmdb_fixed_to_double(int device, double *G_dev, int64_t n, void *stream);
 
+/* ---- multi-GPU: the one exchange step of the sharded direct build ------------------------------------
+ * One process (or thread) per GPU builds its shard with mmdb_fock_direct(..., shard, nshards, ...) into its own G and
+ * then sums the partial matrices: an FP64 sum all-reduce over NCCL (NVLink 5 / NVSwitch).  Rank 0 obtains a unique id
+ * (128 bytes) and hands it to the other ranks through the host program's own rendezvous; every rank then calls
+ * mmdb_comm_init.  fixed_point != 0 reduces the 2^50-scaled 64-bit integers of a deterministic build (flags bit1)
+ * exactly; finish with mmdb_fixed_to_double.  The shard rule (lib.cu screen kernels): KET pair row j of every class
+ * pair belongs to shard j % nshards; rows are ordered by contraction depth, so the deal is cost-balanced. */
+typedef struct mmdb_comm mmdb_comm;
+int mmdb_comm_unique_id(unsigned char *id128);
+int mmdb_comm_init(int device, int nranks, int rank, const unsigned char *id128, mmdb_comm **out);
+int mmdb_allreduce_G(mmdb_comm *comm, double *G_dev, int64_t n, int fixed_point, void *stream);
+int mmdb_comm_destroy(mmdb_comm *comm);
+
 /* Host-buffer convenience forms (the reference-facing calls: host numpy in, host numpy out;
  * H2D/D2H inside).  P, P_old, G are complex128 interleaved (N,N) like the reference's arrays;
  * Q is the reference's triangular table of N(N+1)/2 values keyed p(p+1)/2+q. */
 int mmdb_formPT_host(mmdb_basis *b, const double *P_c128, const double *P_old_c128, double tol,
                      double *G_c128, mmdb_fock_stats *stats);
+/* the two host passes mmdb_formPT_host makes, exported for bindings that stage the planes themselves (multi-GPU):
+ * re/im[x] = P[x] - P_old[x] (cython/fock.pyx:24), *has_im = any non-zero imaginary difference; and the inverse
+ * interleave of the G planes (im may be NULL). */
+int mmdb_c128_diff_split_host(const double *P_c128, const double *P_old_c128, int64_t n, double *re, double *im, int *has_im);
+int mmdb_c128_join_host(const double *re, const double *im, int64_t n, double *out_c128);
 int mmdb_schwarz_host(mmdb_basis *b, double *Q_tri);
 int mmdb_eri_dense_host(mmdb_basis *b, double *TwoE_host);
 

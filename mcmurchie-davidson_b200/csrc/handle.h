@@ -73,5 +73,7 @@ struct mmdb_basis {
     std::vector<cudaEvent_t> ev_pool;             // per-task "list ready" / "list consumed" events of the screening pipeline
     double *scratch_dev = nullptr;
     size_t scratch_cap = 0;   // doubles
+    double *stage_host = nullptr, *stage_dev = nullptr;   // mmdb_formPT_host staging: 4 planes of N^2 doubles each (page-locked / device)
+    size_t stage_n = 0;
 };
 

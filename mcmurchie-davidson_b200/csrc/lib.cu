@@ -121,12 +121,17 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
     cudaFree(b->Dabs_dev); cudaFree(b->DS_dev); cudaFree(b->dglob_dev); cudaFree(b->list_dev);
     cudaFree(b->ctr_dev); cudaFree(b->scratch_dev);
+    if (b->stage_host) cudaFreeHost(b->stage_host);
+    cudaFree(b->stage_dev);
     if (b->aux_stream) { cudaStreamDestroy(b->aux_stream); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
     if (b->scr_stream) { cudaStreamDestroy(b->scr_stream); cudaEventDestroy(b->ev_fork_scr); }
     for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
     delete b;
     return MMDB_OK;
 }
+
+static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *am, const int *nprim, const int *prim_off,
+                             const double *centre, const double *exps, const double *coefs, const int *bf0, double prim_cut);
 
 extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const int *nprim, const int *prim_off,
                                  const double *centre, const double *exps, const double *coefs, const int *bf0,
@@ -141,6 +146,20 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
     CU(cudaSetDevice(device));
     mmdb_basis *b = new mmdb_basis();
     b->device = device;
+    const int rc = basis_create_impl(b, device, nshell, am, nprim, prim_off, centre, exps, coefs, bf0, prim_cut);
+    if (rc != MMDB_OK) {               // every early return of the builder lands here: nothing leaks
+        const std::string msg = mmdb_g_err;
+        mmdb_basis_destroy(b);
+        mmdb_g_err = msg;
+        return rc;
+    }
+    *out = b;
+    return MMDB_OK;
+}
+
+static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *am, const int *nprim, const int *prim_off,
+                             const double *centre, const double *exps, const double *coefs, const int *bf0, double prim_cut)
+{
     b->nshell = nshell;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -148,7 +167,6 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
     int ntot = 0, nbf = 0;
     for (int s = 0; s < nshell; ++s) {
         if (am[s] < 0 || am[s] > MMDB_MAX_AM) {
-            delete b;
             return fail(MMDB_ERR_UNSUPPORTED, "mmdb_basis_create: angular momentum > d is not supported on the device path");
         }
         ShellH h{am[s], nprim[s], prim_off[s], bf0[s], centre[3 * s], centre[3 * s + 1], centre[3 * s + 2]};
@@ -227,7 +245,6 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
         for (auto &h : P.hdr) P.slice_entries += (size_t)((h.pnum + BRA_SLICE - 1) / BRA_SLICE);
         if (P.npairs == 0) continue;
         if ((unsigned)P.npairs > PAIR_MASK) {
-            mmdb_basis_destroy(b);
             return fail(MMDB_ERR_UNSUPPORTED, "more than 2^24 shell pairs in one class");
         }
         std::vector<int> K(P.npairs);
@@ -294,7 +311,6 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
     CU(cudaMalloc(&b->dglob_dev, sizeof(unsigned long long)));
     b->nctr = 4096;
     CU(cudaMalloc(&b->ctr_dev, sizeof(unsigned long long) * b->nctr));
-    *out = b;
     return MMDB_OK;
 }
 
@@ -333,14 +349,12 @@ DECL(0, 0, 0, 0) DECL(1, 0, 0, 0) DECL(1, 0, 1, 0) DECL(1, 1, 0, 0) DECL(1, 1, 1
 DECL(2, 0, 0, 0) DECL(2, 0, 1, 0) DECL(2, 0, 1, 1) DECL(2, 0, 2, 0)
 DECL(2, 1, 0, 0) DECL(2, 1, 1, 0) DECL(2, 1, 1, 1) DECL(2, 1, 2, 0)
 DECL(2, 2, 0, 0) DECL(2, 2, 1, 0)
-DECL(2, 1, 2, 1) DECL(2, 2, 1, 1) DECL(2, 2, 2, 0) DECL(2, 2, 2, 1)
+DECL(2, 1, 2, 1) DECL(2, 2, 1, 1) DECL(2, 2, 2, 0) DECL(2, 2, 2, 1) DECL(2, 2, 2, 2)
 #undef DECL
 }  // namespace mmdb
 
-// every class except (dd|dd) has a class-specialised kernel; (dd|dd) (a few thousand quartets, minutes of
-// compile time when fully unrolled) runs on the generic runtime-L kernel
-static bool has_class_kernel(int la, int lb, int lc, int ld) { return la + lb + lc + ld <= 7; }
-
+// every class (ss|ss) ... (dd|dd) has a class-specialised kernel; the generic runtime-L kernel (impl = 1) is the
+// independent cross-check
 // (la lb) >= (lc ld) in pair-class order is required
 static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a, int epi, int impl, cudaStream_t st)
 {
@@ -349,7 +363,7 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
     const int key = ((la * 3 + lb) * 3 + lc) * 3 + ld;
     cudaError_t e = cudaSuccess;
     const int gridA = b->nsm;   // x occupancy inside launch_class
-    if (impl == 0 && has_class_kernel(la, lb, lc, ld)) {
+    if (impl == 0) {
         switch (key) {
 #define CASE(LA, LB, LC, LD)                                  \
     case ((LA * 3 + LB) * 3 + LC) * 3 + LD:                   \
@@ -359,7 +373,7 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
             CASE(2, 0, 0, 0) CASE(2, 0, 1, 0) CASE(2, 0, 1, 1) CASE(2, 0, 2, 0)
             CASE(2, 1, 0, 0) CASE(2, 1, 1, 0) CASE(2, 1, 1, 1) CASE(2, 1, 2, 0)
             CASE(2, 2, 0, 0) CASE(2, 2, 1, 0)
-            CASE(2, 1, 2, 1) CASE(2, 2, 1, 1) CASE(2, 2, 2, 0) CASE(2, 2, 2, 1)
+            CASE(2, 1, 2, 1) CASE(2, 2, 1, 1) CASE(2, 2, 2, 0) CASE(2, 2, 2, 1) CASE(2, 2, 2, 2)
 #undef CASE
             default:
                 return fail(MMDB_ERR_INVALID, "launch_eri: class not instantiated");
@@ -1055,50 +1069,64 @@ extern "C" int mmdb_eri_dense_host(mmdb_basis *b, double *TwoE_host)
     return r;
 }
 
-__global__ void split_c128_diff_kernel(const double *P, const double *Pold, size_t n, double *re, double *im)
+// Host passes of the reference-facing call: dP = P - P_old (cython/fock.pyx:24) split into real / imaginary planes,
+// and the planes of G interleaved back into the reference's complex128 layout.  One streaming pass each.
+extern "C" int mmdb_c128_diff_split_host(const double *P_c128, const double *P_old_c128, int64_t n, double *re, double *im,
+                                         int *has_im)
 {
-    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
-        re[x] = P[2 * x] - Pold[2 * x];
-        im[x] = P[2 * x + 1] - Pold[2 * x + 1];
+    int any = 0;
+    for (int64_t x = 0; x < n; ++x) {
+        re[x] = P_c128[2 * x] - P_old_c128[2 * x];
+        const double v = P_c128[2 * x + 1] - P_old_c128[2 * x + 1];
+        im[x] = v;
+        any |= (v != 0.0);
     }
+    if (has_im) *has_im = any;
+    return MMDB_OK;
 }
-__global__ void join_c128_kernel(const double *re, const double *im, size_t n, double *out)
+extern "C" int mmdb_c128_join_host(const double *re, const double *im, int64_t n, double *out_c128)
 {
-    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
-        out[2 * x] = re[x];
-        out[2 * x + 1] = im ? im[x] : 0.0;
-    }
+    if (im)
+        for (int64_t x = 0; x < n; ++x) { out_c128[2 * x] = re[x]; out_c128[2 * x + 1] = im[x]; }
+    else
+        for (int64_t x = 0; x < n; ++x) { out_c128[2 * x] = re[x]; out_c128[2 * x + 1] = 0.0; }
+    return MMDB_OK;
 }
 
+static int ensure_stage(mmdb_basis *b)
+{
+    const size_t N2 = (size_t)b->nbf * b->nbf;
+    if (b->stage_n == N2) return MMDB_OK;
+    if (b->stage_host) cudaFreeHost(b->stage_host);
+    if (b->stage_dev) cudaFree(b->stage_dev);
+    b->stage_host = nullptr; b->stage_dev = nullptr; b->stage_n = 0;
+    CU(cudaMallocHost(&b->stage_host, sizeof(double) * N2 * 4));      // [dP re | dP im | G re | G im], page-locked
+    CU(cudaMalloc(&b->stage_dev, sizeof(double) * N2 * 4));
+    b->stage_n = N2;
+    return MMDB_OK;
+}
+
+// formPT with host buffers (cython/fock.pyx:13-87 as the reference's caller sees it): complex128 (N,N) in, complex128
+// un-symmetrised G out.  Staging buffers (page-locked host + device) are cached in the handle; a real density moves
+// one plane each way (8 N^2 bytes), a complex one two.
 extern "C" int mmdb_formPT_host(mmdb_basis *b, const double *P_c128, const double *P_old_c128, double tol,
                                 double *G_c128, mmdb_fock_stats *stats)
 {
     if (!b) return fail(MMDB_ERR_INVALID, "null handle");
     CU(cudaSetDevice(b->device));
-    const size_t N2 = (size_t)b->nbf * b->nbf;
-    double *buf = nullptr;   // [P | Pold | re | im | Gre | Gim] ; P/Pold/out interleaved (2*N2 each)
-    CU(cudaMalloc(&buf, sizeof(double) * N2 * 10));
-    double *dP = buf, *dPo = buf + 2 * N2, *re = buf + 4 * N2, *im = buf + 5 * N2, *Gre = buf + 6 * N2,
-           *Gim = buf + 7 * N2, *Gout = buf + 8 * N2;
-    int r = MMDB_OK;
-    bool has_im = false;
-    for (size_t x = 0; x < N2 && !has_im; ++x) has_im = (P_c128[2 * x + 1] != P_old_c128[2 * x + 1]);
-    cudaError_t e = cudaMemcpy(dP, P_c128, sizeof(double) * 2 * N2, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(dPo, P_old_c128, sizeof(double) * 2 * N2, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(Gre, 0, sizeof(double) * 2 * N2);
-    if (e != cudaSuccess) {
-        cudaFree(buf);
-        return fail(MMDB_ERR_CUDA, cudaGetErrorString(e));
-    }
-    split_c128_diff_kernel<<<b->nsm * 2, 256>>>(dP, dPo, N2, re, im);
-    r = mmdb_fock_direct(b, re, has_im ? im : nullptr, tol, Gre, has_im ? Gim : nullptr, 0, 1, 0, stats, nullptr);
-    if (r == MMDB_OK) {
-        join_c128_kernel<<<b->nsm * 2, 256>>>(Gre, has_im ? Gim : nullptr, N2, Gout);
-        e = cudaMemcpy(G_c128, Gout, sizeof(double) * 2 * N2, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) r = fail(MMDB_ERR_CUDA, cudaGetErrorString(e));
-    }
-    cudaFree(buf);
-    return r;
+    CHK(ensure_stage(b));
+    const size_t N2 = b->stage_n;
+    double *h_re = b->stage_host, *h_im = h_re + N2, *h_Gre = h_re + 2 * N2, *h_Gim = h_re + 3 * N2;
+    double *d_re = b->stage_dev, *d_im = d_re + N2, *d_Gre = d_re + 2 * N2, *d_Gim = d_re + 3 * N2;
+    int has_im = 0;
+    mmdb_c128_diff_split_host(P_c128, P_old_c128, (int64_t)N2, h_re, h_im, &has_im);
+    CU(cudaMemcpyAsync(d_re, h_re, sizeof(double) * N2 * (has_im ? 2 : 1), cudaMemcpyHostToDevice, nullptr));
+    CU(cudaMemsetAsync(d_Gre, 0, sizeof(double) * N2 * (has_im ? 2 : 1), nullptr));
+    CHK(mmdb_fock_direct(b, d_re, has_im ? d_im : nullptr, tol, d_Gre, has_im ? d_Gim : nullptr, 0, 1, 0, stats, nullptr));
+    CU(cudaMemcpyAsync(h_Gre, d_Gre, sizeof(double) * N2 * (has_im ? 2 : 1), cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    mmdb_c128_join_host(h_Gre, has_im ? h_Gim : nullptr, (int64_t)N2, G_c128);
+    return MMDB_OK;
 }
 
 // ------------------------------------------------------------------------------------------

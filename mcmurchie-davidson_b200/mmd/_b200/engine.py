@@ -5,7 +5,9 @@ only the device-buffer carrier and the NCCL plumbing); libmmdb200.so owns the sh
 behind an opaque handle.  All arithmetic happens in the CUDA kernels of csrc/.
 """
 import ctypes as C
+import collections
 import os
+import weakref
 
 import numpy as np
 
@@ -70,10 +72,12 @@ class Engine(object):
             self.pair_flip[sb, sa] = True
             self.pair_flip[sa, sb] = False
         self._schwarz = None
-        self._schwarz_owner_id = None
+        self._resident_screen = None      # the screen object whose values the device currently holds
+        self._resident_len = -1
         self.TwoE_dev = None
         self.last_stats = None
         self._pin = {}
+        self._keepalive = None
         # MMDB_DETERMINISTIC=1: fixed-point integer accumulation of G (bitwise reproducible builds)
         self.deterministic = os.environ.get("MMDB_DETERMINISTIC", "0") not in ("", "0")
 
@@ -148,23 +152,32 @@ class Engine(object):
         p, q = np.tril_indices(N)
         flat = np.ascontiguousarray(Qh[p, q])        # order p(p+1)/2+q
         tab = SchwarzTable(zip(range(len(flat)), flat.tolist()))
-        tab.engine = self
+        tab.engine = weakref.ref(self)    # no strong reference: a table must not keep an evicted engine (and its N^4 tensor) alive
         tab.flat = flat
         self._schwarz = tab
-        self._schwarz_owner_id = id(tab)
+        self._resident_screen = tab
         return tab
 
     def _install_screen(self, screen):
-        """Make sure the device holds the caller's `screen` (dict keyed p(p+1)//2+q, or flat array)."""
+        """Make sure the device holds the caller's `screen` (dict keyed p(p+1)//2+q, or flat array).  The engine
+        remembers WHICH table is resident (`_resident_screen`): its own SchwarzTable object, or the identity of a
+        caller-supplied one, so a later formPT(..., screen=None) re-installs the engine's own table instead of
+        screening with a stale foreign one, and a plain dict is not uploaded again while it stays resident."""
         if screen is None:
             if self._schwarz is None:
                 self.schwarz()
-            return
-        if isinstance(screen, SchwarzTable) and screen.engine is self and self._schwarz_owner_id == id(screen):
-            return
+                return
+            if self._resident_screen is self._schwarz:
+                return
+            screen = self._schwarz
+        if screen is self._resident_screen:
+            if not isinstance(screen, dict) or isinstance(screen, SchwarzTable) or len(screen) == self._resident_len:
+                return
         N = self.N
         ntri = N * (N + 1) // 2
-        if isinstance(screen, dict):
+        if isinstance(screen, SchwarzTable) and screen.flat is not None and len(screen.flat) == ntri:
+            flat = np.ascontiguousarray(screen.flat, dtype=np.float64)
+        elif isinstance(screen, dict):
             flat = np.fromiter((screen[k] for k in range(ntri)), dtype=np.float64, count=ntri)
         else:
             flat = np.ascontiguousarray(screen, dtype=np.float64)
@@ -177,7 +190,8 @@ class Engine(object):
             p, q = np.tril_indices(self.Ndev)
             flat = np.ascontiguousarray(Qd[p, q])
         L.check(self.lib.mmdb_set_schwarz_host(self.h, L.ptr(flat)))
-        self._schwarz_owner_id = id(screen)
+        self._resident_screen = screen           # strong reference: an id() could be recycled by a new object
+        self._resident_len = len(screen) if isinstance(screen, dict) else -1
 
     # ---- dense tensor (cython/twoe.pyx:12-31 doERIs) -------------------------------------------
     def dense(self, keep_device=True):
@@ -206,7 +220,7 @@ class Engine(object):
                 T = TwoE if not isinstance(TwoE, np.ndarray) else torch.from_numpy(np.ascontiguousarray(TwoE)).to(self.tdev)
             else:
                 if self.TwoE_dev is None:
-                    raise L.MMDBError("jk_incore: no device-resident TwoE (call dense() first)")
+                    self.dense(keep_device=True)          # rebuilt rather than failing (e.g. a fresh engine after a cache eviction)
                 T = self.TwoE_dev
             P = np.asarray(P)
             Pre = torch.from_numpy(np.ascontiguousarray(P.real, dtype=np.float64)).to(self.tdev)
@@ -258,7 +272,8 @@ class Engine(object):
 
     def _fock_direct_planes(self, dP, cplx, tol, want_stats, flags):
         """dP: device float64 (nplane, n, n) in device order -> un-symmetrised G planes (device), summed
-        over the torch.distributed ranks (one all-reduce, NCCL over NVLink)."""
+        over the ranks (one all-reduce over NCCL / NVLink: mmdb_allreduce_G of the C ABI on GPUs; the
+        torch.distributed collective only where there is no NCCL, i.e. the gloo CPU tests)."""
         torch = _torch()
         n = self.Ndev
         rank, world = D.world()
@@ -270,11 +285,14 @@ class Engine(object):
         L.check(self.lib.mmdb_fock_direct(self.h, L.ptr(dP[0]), L.ptr(dP[1]) if cplx else None, float(tol), L.ptr(G[0]),
                                           L.ptr(G[1]) if cplx else None, rank, world, int(flags),
                                           C.byref(stats) if want_stats else None, self._stream()))
+        if world > 1:
+            if self.tdev.type == "cuda" and not os.environ.get("MMDB_TORCH_ALLREDUCE"):
+                comm = D.c_abi_comm(self.lib, self.device)
+                L.check(self.lib.mmdb_allreduce_G(comm, L.ptr(G), G.numel(), 1 if self.deterministic else 0, self._stream()))
+            else:
+                D.allreduce_sum_(G.view(torch.int64) if self.deterministic else G)
         if self.deterministic:
-            D.allreduce_sum_(G.view(torch.int64))         # exact: integer sums do not depend on the order
             L.check(self.lib.mmdb_fixed_to_double(self.device, L.ptr(G), G.numel(), self._stream()))
-        else:
-            D.allreduce_sum_(G)
         self._last_stats_raw = stats
         return G
 
@@ -283,30 +301,37 @@ class Engine(object):
         process group with world_size > 1 is initialised (one process per GPU) and sums the partial
         G matrices with one all-reduce (NCCL over NVLink).
 
-        Host side: ONE pass over the inputs (dP = P - P_old, fock.pyx:24, written straight into a page-locked
-        complex staging buffer) and one copy of the result out of the page-locked output buffer; splitting
-        into real / imaginary planes, the "is the density real" test and re-interleaving G happen on the device."""
+        Host side: ONE pass over the inputs (dP = P - P_old, fock.pyx:24, split into page-locked real / imaginary
+        planes by mmdb_c128_diff_split_host) and one pass that interleaves the page-locked G planes into the result.
+        A real density moves one plane each way (8 N^2 bytes H2D, 8 N^2 bytes D2H); nothing synchronises before the
+        final read-back."""
         torch = _torch()
         self._install_screen(screen)
         P = np.asarray(P)
         P_old = np.asarray(P_old)
         n = self.Ndev
-        pin_in, pin_in_np = self._pinned("dP", (n, n), complex)
-        pin_out, pin_out_np = self._pinned("G", (n, n), complex)
-        if self.table.identity:
-            np.subtract(P, P_old, out=pin_in_np)
-        else:
-            pin_in_np[...] = self.table.to_dev_matrix(P - P_old)
+        pin_in, pin_in_np = self._pinned("dP", (2, n, n))
+        pin_out, pin_out_np = self._pinned("G", (2, n, n))
+        if not self.table.identity:
+            P, P_old = self.table.to_dev_matrix(P), self.table.to_dev_matrix(P_old)
+        P = np.ascontiguousarray(P, dtype=np.complex128)
+        P_old = np.ascontiguousarray(P_old, dtype=np.complex128)
+        has_im = C.c_int(0)
+        L.check(self.lib.mmdb_c128_diff_split_host(P.ctypes.data, P_old.ctypes.data, n * n, pin_in_np[0].ctypes.data,
+                                                   pin_in_np[1].ctypes.data, C.byref(has_im)))
+        cplx = bool(has_im.value)
+        npl = 2 if cplx else 1
         with torch.cuda.device(self.tdev):
-            d = torch.view_as_real(pin_in.to(self.tdev, non_blocking=True))      # (n, n, 2)
-            dP = d.permute(2, 0, 1).contiguous()                                 # real and imaginary planes
-            cplx = bool(dP[1].any().item())
+            dP = pin_in[:npl].to(self.tdev, non_blocking=True)
             G = self._fock_direct_planes(dP, cplx, tol, want_stats, flags)
-            Gc = torch.complex(G[0], G[1] if cplx else torch.zeros_like(G[0]))
-            pin_out.copy_(Gc, non_blocking=True)
+            pin_out[:npl].copy_(G, non_blocking=True)
             torch.cuda.current_stream(self.tdev).synchronize()
         self.last_stats = self._last_stats_raw.as_dict() if want_stats else None
-        return self.table.to_user_matrix(pin_out_np.copy())
+        out = np.empty((n, n), dtype=np.complex128)
+        L.check(self.lib.mmdb_c128_join_host(pin_out_np[0].ctypes.data, pin_out_np[1].ctypes.data if cplx else None, n * n,
+                                             out.ctypes.data))
+        self.h2d_bytes = self.d2h_bytes = 8 * n * n * npl          # what this call moved over PCIe (bench.py reports it)
+        return self.table.to_user_matrix(out)
 
     # ---- device-resident variants for the SCF driver (SURVEY 8f rank 3): no host round trip ------
     @property
@@ -365,21 +390,62 @@ class Engine(object):
                 np.ascontiguousarray(M[:, u][:, :, u]), np.ascontiguousarray(Lm[:, u][:, :, u]))
 
 
-# ---- engine cache keyed by the identity of the Basis objects in the list ----------------------
-_CACHE = {}
+# ---- engines -------------------------------------------------------------------------------------------------
+# A Molecule OWNS its engine (mmd/molecule.py keeps it in self._engine, rebuilt by formBasis), so nothing another
+# molecule or an element-wise call does can evict it.  Everything else (the module-level ERI / S / T / V / formPT /
+# doERIs functions called with an arbitrary list of Basis objects) goes through a small LRU cache keyed by the identity
+# of the Basis objects; one entry is evicted at a time, and engines registered by a live Molecule are found first.
+_CACHE = collections.OrderedDict()
+_CACHE_MAX = 8
+_OWNED = weakref.WeakValueDictionary()      # key -> engine owned by a live Molecule
+
+
+def _key(bfs):
+    return tuple(id(b) for b in bfs)
+
+
+def register_owned(bfs, eng):
+    eng._keepalive = list(bfs)
+    _OWNED[_key(bfs)] = eng
+
+
+def owned_engine(bfs):
+    """A fresh engine for a Molecule to own (never shared through the LRU cache)."""
+    eng = Engine(bfs)
+    register_owned(bfs, eng)
+    return eng
 
 
 def engine_for(bfs):
-    key = tuple(id(b) for b in bfs)
-    hit = _CACHE.get(key)
+    key = _key(bfs)
+    hit = _OWNED.get(key)
     if hit is not None:
         return hit
-    if len(_CACHE) > 8:
-        _CACHE.clear()
+    hit = _CACHE.get(key)
+    if hit is not None:
+        _CACHE.move_to_end(key)
+        return hit
     eng = Engine(bfs)
     eng._keepalive = list(bfs)
     _CACHE[key] = eng
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)           # least recently used only
     return eng
+
+
+def engine_containing(fns):
+    """An existing engine whose basis list contains every function of `fns` (by identity) and their positions in
+    it — lets ERI(a,b,c,d) / S / T / V on functions of a molecule reuse the molecule's engine instead of
+    building a new one per distinct tuple (a loop like the reference's mmd/molecule.py:95-99 would otherwise
+    create thousands of engines)."""
+    ids = [id(f) for f in fns]
+    for eng in list(_OWNED.values()) + list(reversed(_CACHE.values())):
+        pos = getattr(eng, "_pos_of", None)
+        if pos is None:
+            pos = eng._pos_of = {id(b): k for k, b in enumerate(eng._keepalive)}
+        if all(i in pos for i in ids):
+            return eng, [pos[i] for i in ids]
+    return None, None
 
 
 def boys(n, T):

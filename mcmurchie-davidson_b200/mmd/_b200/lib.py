@@ -75,6 +75,12 @@ SIGNATURES = {
                                    C.POINTER(FockStats), _vp]),
     "mmdb_fixed_to_double": (C.c_int, [C.c_int, _vp, C.c_int64, _vp]),
     "mmdb_formPT_host": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, C.POINTER(FockStats)]),
+    "mmdb_c128_diff_split_host": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _ip]),
+    "mmdb_c128_join_host": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "mmdb_comm_unique_id": (C.c_int, [_vp]),
+    "mmdb_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "mmdb_allreduce_G": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "mmdb_comm_destroy": (C.c_int, [_vp]),
     "mmdb_schwarz_host": (C.c_int, [_vp, _vp]),
     "mmdb_eri_dense_host": (C.c_int, [_vp, _vp]),
     "mmdb_onee_host": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

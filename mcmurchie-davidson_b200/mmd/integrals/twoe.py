@@ -81,6 +81,9 @@ def ERI(a, b, c, d):
         else:
             uniq.append(x)
             pos.append(len(uniq) - 1)
+    eng, where = _engine.engine_containing(uniq)       # a molecule's (or a cached) engine that already holds them
+    if eng is not None:
+        return float(eng.eri_quartets(np.array([[where[k] for k in pos]]))[0])
     eng = _engine.engine_for(uniq)
     return float(eng.eri_quartets(np.array([pos]))[0])
 

@@ -13,7 +13,7 @@ import numpy as np
 from scipy.linalg import fractional_matrix_power
 
 from mmd._b200 import basisio
-from mmd._b200.engine import engine_for
+from mmd._b200.engine import owned_engine as engine_for
 from mmd.integrals.twoe import Basis, doERIs
 from mmd.scf import SCF
 
@@ -88,6 +88,7 @@ class Molecule(SCF):
     def formBasis(self):
         """self.bfs: atoms in input order -> shells in file order -> Cartesian components."""
         self.bfs = []
+        self._engine = None                # the engine is tied to these Basis objects
         for atom in self.atoms:
             atom_first = len(self.bfs)
             for momentum, prims in self.basis_data[atom.charge]:
@@ -107,7 +108,15 @@ class Molecule(SCF):
     # ---- integrals ---------------------------------------------------------------------------
     @property
     def engine(self):
-        return engine_for(self.bfs)
+        """This molecule's own device engine (shell-pair tables, Schwarz data, the resident TwoE): created on first
+        use, dropped by formBasis when the basis functions change.  Owned here, so no other molecule and no
+        element-wise ERI/S/T/V call can evict it."""
+        eng = getattr(self, "_engine", None)
+        key = tuple(id(b) for b in self.bfs)
+        if eng is None or getattr(self, "_engine_key", None) != key:
+            eng = engine_for(self.bfs)
+            self._engine, self._engine_key = eng, key
+        return eng
 
     def build(self, direct=False):
         self.one_electron_integrals()
