@@ -29,16 +29,93 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "mcmurchie-davidson_b200")
 SAMPLES = os.path.join(ROOT, "bench_samples")
-# dram__bytes_read.sum + dram__bytes_write.sum per class and build (all launches of the class: block-digest and
-# per-function lists), from the ncu --set full capture of the same workload summarised in
-# profiles/r01_ncu_v8_w32_summary.txt.  The traffic is the compact quartet list (8 B/entry) + pair tables; the
-# kernels are FP64-issue bound, not HBM bound.
-NCU_DRAM_BYTES = {"(ss|ss)": 360.3e6, "(ps|ss)": 708.0e6, "(ps|ps)": 345.1e6, "(pp|ss)": 160.2e6, "(pp|ps)": 162.7e6,
-                  "(pp|pp)": 28.1e6, "(ds|ss)": 152.1e6, "(ds|ps)": 148.4e6, "(ds|pp)": 41.1e6, "(ds|ds)": 25.6e6,
-                  "(dp|ss)": 68.3e6, "(dp|ps)": 75.7e6, "(dp|pp)": 26.5e6, "(dp|ds)": 31.1e6, "(dp|dp)": 16.1e6,
-                  "(dd|ss)": 16.9e6, "(dd|ps)": 20.6e6, "(dd|pp)": 9.8e6, "(dd|ds)": 10.8e6, "(dd|dp)": 10.0e6}
 METRIC = "screened_eri_shell_quartets_per_s_direct_fock_build"
 UNIT = "quartets/s"
+WORKLOAD_DESC = {"w32_ccpvdz": "(H2O)32/cc-pVDZ direct RHF Fock build, N=800 Cartesian functions, first-iteration density, tol 1e-12",
+                 "c20h42_631gs": "C20H42/6-31G* direct RHF Fock build, N=384 Cartesian functions, first-iteration density, tol 1e-12",
+                 "w8_ccpvdz": "(H2O)8/cc-pVDZ direct RHF Fock build, N=200 Cartesian functions, first-iteration density, tol 1e-12",
+                 "benzene_631gss": "benzene/6-31G** direct RHF Fock build, N=120 Cartesian functions, first-iteration density, tol 1e-12"}
+
+
+def workload_desc(name):
+    """The SAME string in both arms (ours and --impl reference): the driver compares config.workload."""
+    return WORKLOAD_DESC.get(name, "%s direct RHF Fock build, first-iteration density, tol 1e-12" % name)
+
+
+def ncu_traffic(workload, world, cls):
+    """dram__bytes_read.sum + dram__bytes_write.sum of all launches of one class in one build, read from the committed ncu
+    capture of THIS workload on one GPU (profiles/r02_ncu_dram_<workload>.csv, written by tools/ncu_dram_table.py); None
+    when no capture of this workload / GPU count exists — never a number from another configuration."""
+    if world != 1:
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r02_ncu_dram_%s.csv" % workload)
+    if not os.path.exists(path):
+        return None, None
+    total = 0.0
+    for line in open(path):
+        f = line.strip().split(",")
+        if len(f) >= 3 and f[0] == cls:
+            total += float(f[1]) + float(f[2])
+    return (total if total > 0 else None), os.path.relpath(path, ROOT)
+
+
+# ------------------------------------------------------------------------------------------------
+# un-sampled comparison: ONE complete stock formPT build of H2O/cc-pVDZ (N = 25) by the reference itself
+# ------------------------------------------------------------------------------------------------
+REF_FORMPT_WORKER = r'''
+import json, sys, time
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from mmd.molecule import Molecule
+from mmd.integrals.fock import formPT
+import scipy.linalg
+geom = "\n0 1\nO    0.000000      -0.075791844    0.000000\nH    0.866811829    0.601435779    0.000000\nH   -0.866811829    0.601435779    0.000000\n"
+mol = Molecule(geometry=geom, basis="cc-pvdz")
+t0 = time.perf_counter(); mol.build(direct=True); t_build = time.perf_counter() - t0
+FO = mol.X.T @ mol.Core @ mol.X
+_, CO = scipy.linalg.eigh(FO)
+C = mol.X @ CO
+P = (C[:, :mol.nocc] @ C[:, :mol.nocc].conj().T).astype(complex)
+t0 = time.perf_counter()
+G = formPT(P, np.zeros_like(P), mol.bfs, mol.nbasis, mol.screen, 1e-12)
+dt = time.perf_counter() - t0
+print(json.dumps({"formPT_s": dt, "schwarz_and_onee_s": t_build, "nbasis": mol.nbasis, "G_checksum": float(np.abs(G).sum())}))
+'''
+
+
+def reference_unsampled():
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref, "mmd")):
+        return None
+    out = subprocess.run([sys.executable, "-c", REF_FORMPT_WORKER, ref], capture_output=True, text=True, timeout=600)
+    if out.returncode != 0:
+        return {"error": out.stderr[-300:]}
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    return {"workload": "H2O/cc-pVDZ (N=25) ONE complete stock formPT build, core-guess density, tol 1e-12: no sampling, no extrapolation",
+            "ms_per_build": 1e3 * r["formPT_s"], "fock_builds_per_s": 1.0 / r["formPT_s"], "cores": 1,
+            "G_checksum": r["G_checksum"]}
+
+
+def ours_unsampled(np, Molecule, synth):
+    """The same build through the same reference-facing call (host numpy in / out)."""
+    import scipy.linalg
+    from mmd.integrals.fock import formPT
+    mol = Molecule(synth.water(), "cc-pvdz")
+    mol.build(direct=True)
+    FO = mol.X.T @ mol.Core @ mol.X
+    _, CO = scipy.linalg.eigh(FO)
+    C = mol.X @ CO
+    P = (C[:, :mol.nocc] @ C[:, :mol.nocc].conj().T).astype(complex)
+    Z = np.zeros_like(P)
+    for _ in range(3):
+        G = formPT(P, Z, mol.bfs, mol.nbasis, mol.screen, 1e-12)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        G = formPT(P, Z, mol.bfs, mol.nbasis, mol.screen, 1e-12)
+    dt = (time.perf_counter() - t0) / reps
+    return {"workload": "H2O/cc-pVDZ (N=25) ONE complete stock formPT build, core-guess density, tol 1e-12: no sampling, no extrapolation",
+            "ms_per_build": 1e3 * dt, "fock_builds_per_s": 1.0 / dt, "G_checksum": float(np.abs(G).sum())}
 
 
 def parse():
@@ -193,12 +270,13 @@ def main_reference(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": spec["workload_desc"], "sample": "%d surviving shell quartets (%d contracted integrals) per step, stratified over %d classes" % (
+            "config": {"workload": workload_desc(a.workload), "sample": "%d surviving shell quartets (%d contracted integrals) per step, stratified over %d classes" % (
                 res["n_shell_quartets"], res["n_integrals"], len(res["class_mean_s"]))},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                              "sample": "reference Cython ERI (oracle/_ref) on the stratified quartet sample, %d processes; single-core rate %.1f quartets/s extrapolated by class populations" % (cores, single)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    line["unsampled_h2o_ccpvdz"] = reference_unsampled()
     print(json.dumps(line))
 
 
@@ -365,9 +443,10 @@ def main_ours(a):
         name, c = max(st["classes"].items(), key=lambda kv: kv[1]["ms"])
         fl = c["prim_quartets"] * c["flops_per_prim_quartet"]
         ach = fl / (c["ms"] * 1e-3) / 1e12
+        traffic, traffic_src = ncu_traffic(a.workload, world, name)
         roof = {"bound": "fp64_fma", "kernel": "eri_class_kernel %s fused J/K digestion" % name, "achieved": ach, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": NCU_DRAM_BYTES.get(name),
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of all launches of this class in one build (ncu, profiles/r01_ncu_dram_final_w32.csv); = the 8-byte list entries the class consumes",
+                "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of all launches of this class in one build of this workload on one GPU, %s" % traffic_src) if traffic else "no ncu capture of this workload / GPU count committed: null rather than a number from another configuration",
                 "peak_source": "measured live: DFMA issue probe mmdb_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; nominal 37.2)",
                 "launch_ms": c["ms"], "share_of_step": c["ms"] / sum(x["ms"] + x["screen_ms"] for x in st["classes"].values()),
                 "whole_build": {"model_gflop": mflops / 1e9, "achieved_tflops": mflops / (ms_step * 1e-3) / 1e12,
@@ -376,13 +455,14 @@ def main_ours(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "%s direct RHF Fock build, N=%d Cartesian functions, first-iteration density, tol 1e-12" % (a.workload, N),
+            "config": {"workload": workload_desc(a.workload),
                        "l2": "per-step working set (compact quartet lists, >2 GB) exceeds L2; plus an explicit 512 MiB flush between timed steps",
                        "parallelism": "quartet-sharded x%d + allreduce(G)" % world if world > 1 else "1 GPU"},
             "fock_builds_per_s": 1e3 / ms_step, "prim_quartets_per_s": primq / (ms_step * 1e-3),
             "contracted_integrals_per_s": fnq / (ms_step * 1e-3), "quartets_per_build": quartets,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N * N, "d2h_bytes_per_step": 8 * N * N,
-                    "ms_per_step": 1e3 * float(tt.item()), "max_abs_diff_vs_device_path": parity},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(eng.h2d_bytes), "d2h_bytes_per_step": int(eng.d2h_bytes),
+                    "ms_per_step": 1e3 * float(tt.item()),
+                    "max_abs_diff_host_call_vs_device_call_same_sharding": parity},
             "gpu_launches": launches * a.steps, "clocks": clk, "roofline": roof,
             "classes": {k: {"quartets": v["quartets"], "prim_quartets": v["prim_quartets"], "ms": round(v["ms"], 4),
                             "screen_ms": round(v["screen_ms"], 4),
@@ -392,8 +472,13 @@ def main_ours(a):
     if world == 1:
         try:
             line["incore_config2"] = incore_bench(E, L, synth, Molecule, np, torch, C)
+            line["roofline_incore"] = line["incore_config2"]["roofline"]       # HBM-bound kernel of BASELINE config 2
         except Exception as exc:      # the direct-build line must not be lost to an in-core failure
             line["incore_config2"] = {"error": str(exc)[:200]}
+        try:
+            line["unsampled_h2o_ccpvdz"] = ours_unsampled(np, Molecule, synth)
+        except Exception as exc:
+            line["unsampled_h2o_ccpvdz"] = {"error": str(exc)[:200]}
     # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
     if world == 1 and a.cpu_baseline:
         sample = load_sample(a.workload)

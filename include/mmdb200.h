@@ -100,12 +100,14 @@ typedef struct {
     int64_t prim_quartets;    /* primitive shell quartets evaluated                              */
     int64_t fn_quartets;      /* contracted basis-function quartets produced                     */
     int64_t slow_quartets;    /* of `quartets`: digested per function (diagonal-type / complex)  */
-    int64_t launches;         /* kernels launched by this call (2 density screens + 3 per class-pair chunk) */
+    int64_t launches;         /* kernels launched by this call (2 density screens + 4 per class-pair chunk) */
     double model_flops;       /* sum over classes of prim_quartets(class) * F(class), SURVEY §8d */
     int64_t class_quartets[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];
     int64_t class_prim_quartets[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];
     float class_ms[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR];        /* ERI+digestion kernel time per class (flags bit0) */
     float class_screen_ms[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR]; /* screening kernel time per class (flags bit0)     */
+    int64_t far_entries;      /* list entries (virtual bra pair, ket pair) on the far-field lists: every primitive quartet asymptotic */
+    int64_t near_entries;     /* block-digestible list entries with at least one primitive quartet in the tabulated Boys range */
 } mmdb_fock_stats;
 
 /* Direct Fock build (cython/fock.pyx:13-87): G += contributions of every canonical basis-function

@@ -173,19 +173,23 @@ __host__ __device__ constexpr int boys_tmax_i(int L)
 }
 __host__ __device__ constexpr int boys_rows(int L) { return boys_tmax_i(L) * 8 + 1; }
 
-// 1/sqrt(x) to full double precision without the slow-path branches of the library routine:
-// MUFU.RSQ64H seed (2^-22) + two Newton steps.  x is a sum of exponents or a Boys argument >= 60 here.
+// 1/sqrt(x) to full double precision without the slow-path branches of the library routine: MUFU.RSQ64H seed
+// (relative error <= 2^-20) + ONE third-order step  y (1 + e/2 + 3e^2/8),  e = 1 - x y^2  (error 5e^3/16 < 2^-58):
+// five FP64 instructions with a dependent depth of four, instead of seven / six for two Newton steps.
+// x is a sum of exponents, a squared distance or a Boys argument here (normal range, never 0 on the paths that use it).
 __device__ __forceinline__ double fast_rsqrt(double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double h = 0.5 * x;
-    double e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    e = fma(-h * y, y, 0.5);
-    y = fma(y, e, y);
-    return y;
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = y * e;
+    return fma(q, p, y);
 }
+// sqrt(pi)/2 is folded into the pair coefficients (each PrimPair::cc carries its square root, lib.cu) and its
+// inverse into the Boys tables, so neither Boys branch of the class kernels multiplies by it.
+constexpr double SQRTPI_2 = 0.88622692545275801365;
 constexpr int BOYS_MAXL = 8;
 
 // ------------------------------------------------------------------------------------------
@@ -246,6 +250,7 @@ __device__ __forceinline__ void boys_eval_rt(int L, double T, const double *__re
             const double t2 = T + T;
             for (int m = L; m > 0; --m) F[m - 1] = fma(t2, F[m], e) / (double)(2 * m - 1);
         }
+        for (int m = 0; m <= L; ++m) F[m] *= SQRTPI_2;      // the tables carry 2/sqrt(pi)
     } else {
         const double rt = fast_rsqrt(T);
         F[0] = 0.88622692545275801365 * rt;
@@ -360,15 +365,14 @@ __device__ __forceinline__ void build_R_impl(RS &R, const double (&Fs)[L + 1], d
 // (sqrt(alpha)) to undo the normalisation.
 // Fs[n] = s (-2 alpha)^n F_n(alpha |PQ|^2), the seeds of the R recursion, for one primitive quartet (both Boys
 // branches; this is the routine mmdb_boys_class_host probes, per L, across its own T_max(L) switch)
-template <int L>
+template <int L, bool FAR = false>
 __device__ __forceinline__ void prim_Fs(double (&Fs)[L + 1], double pb, double pk, double ccb, double cck, double R2,
                                         const double *__restrict__ boys_tab)
 {
-    const double pp = pb * pk, ps = pb + pk;
     const double c2 = ccb * cck;
-    if (pp * R2 >= (double)boys_tmax_i(L) * ps) {
+    auto asym = [&]() {
         const double ri = fast_rsqrt(R2);
-        Fs[0] = (0.88622692545275801365 * c2) * ri;
+        Fs[0] = c2 * ri;
         if constexpr (L > 0) {
             const double nr2 = -(ri * ri);
             sfor<0, L>([&](auto I) {
@@ -376,24 +380,33 @@ __device__ __forceinline__ void prim_Fs(double (&Fs)[L + 1], double pb, double p
                 Fs[m + 1] = ((2 * m + 1) * nr2) * Fs[m];
             });
         }
+    };
+    if constexpr (FAR) {
+        // the screening kernel has proved alpha |PQ|^2 >= T_max(L) for EVERY primitive quartet of this list entry
+        asym();
     } else {
-        const double rs = fast_rsqrt(ps);        // one reciprocal square root serves 1/(p+q) and 1/sqrt(p+q)
-        const double alpha = pp * (rs * rs);
-        boys_table<L>(alpha * R2, boys_tab, Fs);
-        double s = c2 * (alpha * fast_rsqrt(alpha));     // ccb cck sqrt(p q) / sqrt(p+q)
-        const double m2a = -2.0 * alpha;
+        const double pp = pb * pk, ps = pb + pk;
+        if (pp * R2 >= (double)boys_tmax_i(L) * ps) {
+            asym();
+        } else {
+            const double rs = fast_rsqrt(ps);        // one reciprocal square root serves 1/(p+q) and 1/sqrt(p+q)
+            const double alpha = pp * (rs * rs);
+            boys_table<L>(alpha * R2, boys_tab, Fs);     // (2/sqrt(pi)) F_m: undoes the sqrt(pi)/2 inside c2
+            double s = c2 * (alpha * fast_rsqrt(alpha));     // ccb cck sqrt(p q) / sqrt(p+q)
+            const double m2a = -2.0 * alpha;
 #pragma unroll
-        for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
+            for (int n = 0; n <= L; ++n) { Fs[n] *= s; s *= m2a; }
+        }
     }
 }
 
-template <int L, class RS>
+template <int L, bool FAR = false, class RS>
 __device__ __forceinline__ void prim_R(RS &R, double pb, double pk, double ccb, double cck, double X, double Y, double Z,
                                        const double *__restrict__ boys_tab)
 {
     const double R2 = X * X + Y * Y + Z * Z;
     double Fs[L + 1];
-    prim_Fs<L>(Fs, pb, pk, ccb, cck, R2, boys_tab);
+    prim_Fs<L, FAR>(Fs, pb, pk, ccb, cck, R2, boys_tab);
     build_R_impl<L>(R, Fs, X, Y, Z);
 }
 
@@ -403,7 +416,7 @@ __device__ __forceinline__ void prim_R_asym(RS &R, double c2, double R2, double 
 {
     double Fs[L + 1];
     const double ri = fast_rsqrt(R2);
-    Fs[0] = (0.88622692545275801365 * c2) * ri;
+    Fs[0] = c2 * ri;
     if constexpr (L > 0) {
         const double nr2 = -(ri * ri);
         sfor<0, L>([&](auto I) {
@@ -416,19 +429,56 @@ __device__ __forceinline__ void prim_R_asym(RS &R, double c2, double R2, double 
 
 // out-of-line copy for the shared-memory variant: the (long) recursion is emitted once per kernel
 // instead of once per ket-component chunk
-template <int L>
+template <int L, bool FAR = false>
 __device__ __noinline__ void prim_R_smem(double *base, int stride, double pb, double pk, double ccb, double cck, double X,
                                          double Y, double Z, const double *__restrict__ boys_tab)
 {
     RStore<L, true> R{base, stride};
-    prim_R<L>(R, pb, pk, ccb, cck, X, Y, Z, boys_tab);
+    prim_R<L, FAR>(R, pb, pk, ccb, cck, X, Y, Z, boys_tab);
+}
+
+// ---- compile-time layout of the signed ket coefficient products of one chunk (R-major ket transform) -------------------
+template <int LC, int LD>
+__host__ __device__ constexpr int ket_box(int cd, int dim)
+{
+    return cart_pow(LC, cd / ncart(LD), dim) + cart_pow(LD, cd % ncart(LD), dim);
+}
+template <int LC, int LD, int CD0>
+__host__ __device__ constexpr int ket_coef_off(int cdi, int tau, int nu, int phi)
+{
+    int off = 0;
+    for (int x = 0; x < cdi; ++x)
+        off += (ket_box<LC, LD>(CD0 + x, 0) + 1) * (ket_box<LC, LD>(CD0 + x, 1) + 1) * (ket_box<LC, LD>(CD0 + x, 2) + 1);
+    const int ny = ket_box<LC, LD>(CD0 + cdi, 1) + 1, nz = ket_box<LC, LD>(CD0 + cdi, 2) + 1;
+    return off + (tau * ny + nu) * nz + phi;
+}
+template <int LC, int LD, int CD0, int NCDC>
+__host__ __device__ constexpr int ket_ncoef()
+{
+    int off = 0;
+    for (int x = 0; x < NCDC; ++x)
+        off += (ket_box<LC, LD>(CD0 + x, 0) + 1) * (ket_box<LC, LD>(CD0 + x, 1) + 1) * (ket_box<LC, LD>(CD0 + x, 2) + 1);
+    return off;
+}
+// does R[KT,KU,KV] feed any G element of this chunk?
+template <int LC, int LD, int CD0, int NCDC, int LBRA>
+__host__ __device__ constexpr bool ket_uses_R(int KT, int KU, int KV)
+{
+    for (int x = 0; x < NCDC; ++x) {
+        const int ex = ket_box<LC, LD>(CD0 + x, 0), ey = ket_box<LC, LD>(CD0 + x, 1), ez = ket_box<LC, LD>(CD0 + x, 2);
+        for (int tau = 0; tau <= (KT < ex ? KT : ex); ++tau)
+            for (int nu = 0; nu <= (KU < ey ? KU : ey); ++nu)
+                for (int phi = 0; phi <= (KV < ez ? KV : ez); ++phi)
+                    if ((KT - tau) + (KU - nu) + (KV - phi) <= LBRA) return true;
+    }
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------
 // One contracted shell quartet, ket component pairs [CD0, CD0+NCDC), class-specialised.
 // out[ab*NCDC + cdi] accumulates (ab|cd) WITHOUT the per-component normalisation.
 // ------------------------------------------------------------------------------------------
-template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SERIAL_CHUNKS>
+template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SERIAL_CHUNKS, bool FAR = false>
 __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraSrc &bsrc,
                                                    const PairHdr &kh, const PrimPair *__restrict__ kp,
                                                    const double *__restrict__ boys_tab, double *r_smem, int r_stride,
@@ -456,6 +506,66 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                 build_E<LC, LD>(Ek, QC, QD, 0.5 / k.p);
             }
             // ket Hermite -> Cartesian:  G[tuv][cd] += (-1)^(tau+nu+phi) E^cd_tau E^cd_nu E^cd_phi R[t+tau,u+nu,v+phi]
+            if constexpr (RSMEM) {
+                // R lives in shared memory: R-major ("scatter") order.  The signed coefficient products of the chunk are
+                // formed first (registers), then every R element is loaded ONCE and added into all the G elements it
+                // feeds — the cd-major order made the compiler keep dozens of R values live across the chunk (or load
+                // them again), which is where the 255-register kernels and their spills came from.
+                constexpr int NCO = ket_ncoef<LC, LD, CD0, NCDC>();
+                double co[NCO];
+                sfor<0, NCDC>([&](auto CDI) {
+                    constexpr int cdi = decltype(CDI)::value;
+                    constexpr int cd = CD0 + cdi;
+                    constexpr int c = cd / ND, d = cd % ND;
+                    constexpr int ex = cart_pow(LC, c, 0) + cart_pow(LD, d, 0), ey = cart_pow(LC, c, 1) + cart_pow(LD, d, 1),
+                                  ez = cart_pow(LC, c, 2) + cart_pow(LD, d, 2);
+                    sfor<0, ex + 1>([&](auto TAU) {
+                        constexpr int tau = decltype(TAU)::value;
+                        sfor<0, ey + 1>([&](auto NU) {
+                            constexpr int nu = decltype(NU)::value;
+                            const double exy = Ek.v[0][cart_pow(LC, c, 0)][cart_pow(LD, d, 0)][tau] * Ek.v[1][cart_pow(LC, c, 1)][cart_pow(LD, d, 1)][nu];
+                            sfor<0, ez + 1>([&](auto PHI) {
+                                constexpr int phi = decltype(PHI)::value;
+                                double coef = exy * Ek.v[2][cart_pow(LC, c, 2)][cart_pow(LD, d, 2)][phi];
+                                if constexpr ((tau + nu + phi) & 1) coef = -coef;
+                                co[ket_coef_off<LC, LD, CD0>(cdi, tau, nu, phi)] = coef;
+                            });
+                        });
+                    });
+                });
+                sfor<0, L + 1>([&](auto KT_) {
+                    constexpr int KT = decltype(KT_)::value;
+                    sfor<0, L - KT + 1>([&](auto KU_) {
+                        constexpr int KU = decltype(KU_)::value;
+                        sfor<0, L - KT - KU + 1>([&](auto KV_) {
+                            constexpr int KV = decltype(KV_)::value;
+                            if constexpr (ket_uses_R<LC, LD, CD0, NCDC, LBRA>(KT, KU, KV)) {
+                                const double r = R[hidx(KT, KU, KV)];
+                                sfor<0, NCDC>([&](auto CDI) {
+                                    constexpr int cdi = decltype(CDI)::value;
+                                    constexpr int cd = CD0 + cdi;
+                                    constexpr int c = cd / ND, d = cd % ND;
+                                    constexpr int ex = cart_pow(LC, c, 0) + cart_pow(LD, d, 0), ey = cart_pow(LC, c, 1) + cart_pow(LD, d, 1),
+                                                  ez = cart_pow(LC, c, 2) + cart_pow(LD, d, 2);
+                                    sfor<0, (KT < ex ? KT : ex) + 1>([&](auto TAU) {
+                                        constexpr int tau = decltype(TAU)::value;
+                                        sfor<0, (KU < ey ? KU : ey) + 1>([&](auto NU) {
+                                            constexpr int nu = decltype(NU)::value;
+                                            sfor<0, (KV < ez ? KV : ez) + 1>([&](auto PHI) {
+                                                constexpr int phi = decltype(PHI)::value;
+                                                constexpr int t = KT - tau, u = KU - nu, v = KV - phi;
+                                                if constexpr (t + u + v <= LBRA)
+                                                    G[hidx(t, u, v) * NCDC + cdi] =
+                                                        fma(co[ket_coef_off<LC, LD, CD0>(cdi, tau, nu, phi)], r, G[hidx(t, u, v) * NCDC + cdi]);
+                                            });
+                                        });
+                                    });
+                                });
+                            }
+                        });
+                    });
+                });
+            } else {
             sfor<0, NCDC>([&](auto CDI) {
                 constexpr int cdi = decltype(CDI)::value;
                 constexpr int cd = CD0 + cdi;
@@ -486,6 +596,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                     });
                 });
             });
+            }
         };
         auto ket_body = [&](const PrimPair &k) {
             const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
@@ -496,9 +607,9 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                 // a quartet with ONE primitive quartet keeps its R table in shared memory across the
                 // ket-component chunks: only the first chunk builds it
                 if (!SERIAL_CHUNKS || CD0 == 0 || (ib1 - ib0) * kh.pnum != 1)
-                    prim_R_smem<L>(r_smem, r_stride, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
+                    prim_R_smem<L, FAR>(r_smem, r_stride, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
             } else {
-                prim_R<L>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
+                prim_R<L, FAR>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
             }
             ket_transform(R, k);
         };
@@ -511,10 +622,15 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
             const double Xa = b.Px - ka.Px, Ya = b.Py - ka.Py, Za = b.Pz - ka.Pz;
             const double Xc = b.Px - kc.Px, Yc = b.Py - kc.Py, Zc = b.Pz - kc.Pz;
             const double R2a = Xa * Xa + Ya * Ya + Za * Za, R2c = Xc * Xc + Yc * Yc + Zc * Zc;
-            const double tm = (double)boys_tmax_i(L);
-            const bool asym = ((b.p * ka.p) * R2a >= tm * (b.p + ka.p)) && ((b.p * kc.p) * R2c >= tm * (b.p + kc.p));
-            const unsigned act = __activemask();
-            if (__all_sync(act, asym)) {
+            bool both;
+            if constexpr (FAR) {
+                both = true;         // every primitive quartet of a far-list entry is on the asymptotic branch
+            } else {
+                const double tm = (double)boys_tmax_i(L);
+                const bool asym = ((b.p * ka.p) * R2a >= tm * (b.p + ka.p)) && ((b.p * kc.p) * R2c >= tm * (b.p + kc.p));
+                both = __all_sync(__activemask(), asym);
+            }
+            if (both) {
                 RStore<L, false> Ra, Rc;
                 prim_R_asym<L>(Ra, b.cc * ka.cc, R2a, Xa, Ya, Za);
                 prim_R_asym<L>(Rc, b.cc * kc.cc, R2c, Xc, Yc, Zc);

@@ -56,10 +56,13 @@ __host__ __device__ constexpr bool block_chunks()
 // Boys table, and five or six copies per SM left the L1 cache with a few tens of KB (ncu: 37% L1 hit rate
 // on the primitive-pair, header and density loads, long-scoreboard stalls on the first use of each load).
 // The L >= 3 classes keep 128-thread CTAs (they synchronise per quartet, see LOCKSTEP below).
-template <int LA, int LB, int LC, int LD>
+template <int LA, int LB, int LC, int LD, bool FAR = false>
 __host__ __device__ constexpr int ka_threads()
 {
     constexpr int L = LA + LB + LC + LD;
+    // far-list kernels stage no Boys table, so nothing is gained by one huge CTA per SM: 256-thread CTAs, as many
+    // as the register budget of min_blocks allows
+    if (FAR && L <= 2) return 256;
     if (L == 0) return 768;                      // 80 registers
     if (L == 1) return 640;                      // 96 registers (768 threads at 80 registers: slower)
     if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
@@ -72,18 +75,24 @@ __host__ __device__ constexpr int ka_threads()
 }
 
 // minimum co-resident CTAs per SM the compiler must allow for (register cap = 65536 / (threads * MINB))
-template <int LA, int LB, int LC, int LD>
+template <int LA, int LB, int LC, int LD, bool FAR = false>
 __host__ __device__ constexpr int min_blocks()
 {
     constexpr int L = LA + LB + LC + LD;
+    if (FAR && L == 0) return 4;                 // <= 64 registers
+    if (FAR && L == 1) return 3;                 // <= 80 registers
+    if (FAR && L == 2) return (LA == 2) ? 2 : 1; // (ds|ss) <= 128 registers; (ps|ps), (pp|ss) as the register use falls
+#ifdef MMDB_MINB
+    if (L >= 3) return MMDB_MINB;       // experiment switch
+#endif
     return (L <= 2 || ka_threads<LA, LB, LC, LD>() == 256) ? 1 : 2;     // measured: tighter caps on the L >= 3 classes only add spills
 }
 
-template <int LA, int LB, int LC, int LD>
+template <int LA, int LB, int LC, int LD, bool FAR = false>
 __host__ __device__ constexpr size_t class_smem_bytes()
 {
-    size_t b = (size_t)boys_rows(LA + LB + LC + LD) * BOYS_STRIDE * sizeof(double);
-    if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(LA + LB + LC + LD) * ka_threads<LA, LB, LC, LD>() * sizeof(double);
+    size_t b = FAR ? 0 : (size_t)boys_rows(LA + LB + LC + LD) * BOYS_STRIDE * sizeof(double);
+    if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(LA + LB + LC + LD) * ka_threads<LA, LB, LC, LD, FAR>() * sizeof(double);
     return b;
 }
 
@@ -360,7 +369,7 @@ static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, cons
     }
 }
 
-template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC, bool SERIAL_CHUNKS>
+template <int LA, int LB, int LC, int LD, int EPI, int CD0, int NCDC, bool SERIAL_CHUNKS, bool FAR>
 __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e, unsigned ibra, bool valid, const PairHdr &bh,
                                           const PairHdr &kh, const double *boys_tab, bool samePair, bool ket_uniform,
                                           int ib0, int ib1)
@@ -369,9 +378,10 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     constexpr int NAB = NA * NB, NCD = NC * ND;
     double out[NAB * NCDC];
     if (valid)
-        eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS>(
-            bh, BraSrc{a.braS, a.braRow, a.braN, ibra}, kh, a.ketP, boys_tab, const_cast<double *>(boys_tab) + boys_rows(LA + LB + LC + LD) * BOYS_STRIDE + threadIdx.x,
-            ka_threads<LA, LB, LC, LD>(), ib0, ib1, out);
+        eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS, FAR>(
+            bh, BraSrc{a.braS, a.braRow, a.braN, ibra}, kh, a.ketP, boys_tab,
+            const_cast<double *>(boys_tab) + (FAR ? 0 : boys_rows(LA + LB + LC + LD) * BOYS_STRIDE) + threadIdx.x,
+            ka_threads<LA, LB, LC, LD, FAR>(), ib0, ib1, out);
     if constexpr (EPI == EPI_STORE) {
         if (valid) {
             double *o = a.out + e * (unsigned long long)(NAB * NCD);
@@ -415,8 +425,11 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     }
 }
 
-template <int LA, int LB, int LC, int LD, int EPI>
-__global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, LB, LC, LD>()) eri_class_kernel(const EriArgs a)
+// FAR = true: the far-field list of a direct build — the screening kernel has proved that every primitive quartet of
+// every entry is on the asymptotic Boys branch (alpha |PQ|^2 >= T_max(L)), so this variant has no Boys table in shared
+// memory, no branch and no table code: fewer registers, more resident warps, branch-uniform warps.
+template <int LA, int LB, int LC, int LD, int EPI, bool FAR = false>
+__global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD, FAR>(), min_blocks<LA, LB, LC, LD, FAR>()) eri_class_kernel(const EriArgs a)
 {
     constexpr int NCD = ncart(LC) * ncart(LD);
     constexpr int NCDC = chunk_ncd<LA, LB, LC, LD>();
@@ -428,8 +441,10 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, L
         const unsigned long long first = (BC ? blockIdx.x / NCHUNK : blockIdx.x) * (unsigned long long)blockDim.x;
         if (first >= n) return;
     }
-    for (int x = threadIdx.x; x < boys_rows(LA + LB + LC + LD) * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
-    __syncthreads();
+    if constexpr (!FAR) {
+        for (int x = threadIdx.x; x < boys_rows(LA + LB + LC + LD) * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
+        __syncthreads();
+    }
     // Block-uniform trip count: every warp stays in the loop (the digestion uses warp shuffles) and, for the
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
     // barrier per quartet so they stream through the code together (one fetch serves all of them).
@@ -454,26 +469,25 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, L
             if constexpr (LOCKSTEP) __syncthreads();
             const unsigned long long e = base + threadIdx.x;
             const bool valid = e < n;
-            uint2 ij = ij_next;
-            const int slice = (EPI == EPI_STORE) ? 0 : (int)(ij.x >> SLICE_SHIFT);
-            if constexpr (EPI != EPI_STORE) ij.x &= PAIR_MASK;
+            const uint2 ij = ij_next;
+            // direct builds: ij.x indexes the class's VIRTUAL bra pairs (one slice of <= BRA_SLICE primitive pairs of a
+            // shell pair, lib.cu build_virtual_pairs), whose header carries the slice's own primitive range
             const PairHdr bh = ld_hdr(a.braH + ij.x);
             const PairHdr kh = ld_hdr(a.ketH + ij.y);
             if (base + wstride < n) ij_next = __ldg(a.list + (long long)min(e + wstride, n - 1) * lstep);
-            const bool samePair = a.same_class && (ij.x == ij.y);
-            const int ib0 = (EPI == EPI_STORE) ? 0 : slice * BRA_SLICE;
-            const int ib1 = (EPI == EPI_STORE) ? bh.pnum : min(bh.pnum, ib0 + BRA_SLICE);
+            const bool samePair = a.same_class && (bh.pad0 == (int)ij.y);       // pad0: (parent) pair index of the bra entry
+            const int ib0 = 0, ib1 = bh.pnum;
             bool ket_uniform = false;
             if constexpr (EPI == EPI_DIGEST) {
                 const unsigned y0 = __shfl_sync(0xffffffffu, ij.y, 0);
                 ket_uniform = __all_sync(0xffffffffu, ij.y == y0) && __all_sync(0xffffffffu, valid);
             }
             if constexpr (chsel >= 0) {
-                run_chunk<LA, LB, LC, LD, EPI, chsel * NCDC, NCDC, false>(a, e, ij.x, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
+                run_chunk<LA, LB, LC, LD, EPI, chsel * NCDC, NCDC, false, FAR>(a, e, ij.x, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
             } else {
                 sfor<0, NCHUNK>([&](auto CH) {
                     constexpr int ch = decltype(CH)::value;
-                    run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC, true>(a, e, ij.x, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
+                    run_chunk<LA, LB, LC, LD, EPI, ch * NCDC, NCDC, true, FAR>(a, e, ij.x, valid, bh, kh, s_boys, samePair, ket_uniform, ib0, ib1);
                 });
             }
         }
@@ -490,50 +504,57 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD>(), min_blocks<LA, L
 
 // host launcher, defined (explicitly instantiated) in inst_*.cu
 template <int LA, int LB, int LC, int LD>
-cudaError_t launch_class(const EriArgs &a, int epi, int grid, cudaStream_t st);
+cudaError_t launch_class(const EriArgs &a, int kind, int grid, cudaStream_t st);
+
+// launch kinds: the three epilogues + the far-field variant of the block digestion
+enum { LK_STORE = 0, LK_DIGEST = 1, LK_DIGEST_SLOW = 2, LK_DIGEST_FAR = 3, LK_COUNT = 4 };
+
+template <int LA, int LB, int LC, int LD, int EPI, bool FAR>
+static void setup_kernel(int *occ)
+{
+    constexpr size_t smem = class_smem_bytes<LA, LB, LC, LD, FAR>();
+    constexpr int threads = ka_threads<LA, LB, LC, LD, FAR>();
+    auto k = eri_class_kernel<LA, LB, LC, LD, EPI, FAR>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // persistent grid: as many CTAs as are co-resident (occupancy x SM count)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, threads, smem);
+    if (*occ < 1) *occ = 1;
+    // shared-memory carve-out: just what the resident CTAs need, the rest of the 256 KB stays L1
+    const int pct = (int)std::min<size_t>(100, (smem * *occ + 1024 * *occ) * 100 / (228 * 1024) + 3);
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
 
 template <int LA, int LB, int LC, int LD>
-cudaError_t launch_class_impl(const EriArgs &a, int epi, int grid, cudaStream_t st)
+cudaError_t launch_class_impl(const EriArgs &a, int kind, int grid, cudaStream_t st)
 {
-    constexpr size_t smem = class_smem_bytes<LA, LB, LC, LD>();
-    constexpr int threads = ka_threads<LA, LB, LC, LD>();
-    static int occ[3] = {0, 0, 0};
+    static int occ[LK_COUNT] = {0, 0, 0, 0};
     if (occ[0] == 0) {
-        if (smem > 48 * 1024) {
-            cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        }
-        // persistent grid: as many CTAs as are co-resident (occupancy x SM count); `grid` carries the SM count
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, threads, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, threads, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, threads, smem);
-        for (int &o : occ)
-            if (o < 1) o = 1;
-        // shared-memory carve-out: just what the resident CTAs need, the rest of the 256 KB stays L1
-        const int pct[3] = {(int)std::min<size_t>(100, (smem * occ[0] + 1024 * occ[0]) * 100 / (228 * 1024) + 3),
-                            (int)std::min<size_t>(100, (smem * occ[1] + 1024 * occ[1]) * 100 / (228 * 1024) + 3),
-                            (int)std::min<size_t>(100, (smem * occ[2] + 1024 * occ[2]) * 100 / (228 * 1024) + 3)};
-        cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_STORE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct[0]);
-        cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST>, cudaFuncAttributePreferredSharedMemoryCarveout, pct[1]);
-        cudaFuncSetAttribute(eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW>, cudaFuncAttributePreferredSharedMemoryCarveout, pct[2]);
+        setup_kernel<LA, LB, LC, LD, EPI_STORE, false>(&occ[LK_STORE]);
+        setup_kernel<LA, LB, LC, LD, EPI_DIGEST, false>(&occ[LK_DIGEST]);
+        setup_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW, false>(&occ[LK_DIGEST_SLOW]);
+        setup_kernel<LA, LB, LC, LD, EPI_DIGEST, true>(&occ[LK_DIGEST_FAR]);
     }
     constexpr int NCH = block_chunks<LA, LB, LC, LD>() ? ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() : 1;
     auto shape = [&](int o) { return std::max(NCH, (grid * o) / NCH * NCH); };   // multiple of the chunk count
-    if (epi == EPI_STORE)
-        eri_class_kernel<LA, LB, LC, LD, EPI_STORE><<<shape(occ[0]), threads, smem, st>>>(a);
-    else if (epi == EPI_DIGEST)
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST><<<shape(occ[1]), threads, smem, st>>>(a);
+    constexpr int threads = ka_threads<LA, LB, LC, LD, false>();
+    constexpr size_t smem = class_smem_bytes<LA, LB, LC, LD, false>();
+    if (kind == LK_STORE)
+        eri_class_kernel<LA, LB, LC, LD, EPI_STORE, false><<<shape(occ[kind]), threads, smem, st>>>(a);
+    else if (kind == LK_DIGEST)
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST, false><<<shape(occ[kind]), threads, smem, st>>>(a);
+    else if (kind == LK_DIGEST_SLOW)
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW, false><<<shape(occ[kind]), threads, smem, st>>>(a);
     else
-        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW><<<shape(occ[2]), threads, smem, st>>>(a);
+        eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST, true><<<shape(occ[kind]), ka_threads<LA, LB, LC, LD, true>(),
+                                                             class_smem_bytes<LA, LB, LC, LD, true>(), st>>>(a);
     return cudaGetLastError();
 }
 
 #define MMDB_INSTANTIATE_CLASS(LA, LB, LC, LD)                                                            \
     template <>                                                                                          \
-    cudaError_t launch_class<LA, LB, LC, LD>(const EriArgs &a, int epi, int grid, cudaStream_t st)       \
+    cudaError_t launch_class<LA, LB, LC, LD>(const EriArgs &a, int kind, int grid, cudaStream_t st)      \
     {                                                                                                    \
-        return launch_class_impl<LA, LB, LC, LD>(a, epi, grid, st);                                      \
+        return launch_class_impl<LA, LB, LC, LD>(a, kind, grid, st);                                     \
     }
 
 }  // namespace mmdb

@@ -1,6 +1,5 @@
-// kernels_b.cuh — generic (runtime angular momentum) shell-quartet kernel.
-// Used for (dd|dd) (a few thousand quartets of the target workloads; minutes of compile time when fully
-// unrolled) and as an independent cross-check of the class-specialised kernels (impl = 1).  One thread per (shell quartet, ket component pair); R, E and the Hermite
+// kernels_b.cuh — generic (runtime angular momentum) shell-quartet kernel: the independent cross-check of the
+// class-specialised kernels (impl = 1 of mmdb_eri_shell_quartets; it stores integrals, it does not digest).  One thread per (shell quartet, ket component pair); R, E and the Hermite
 // intermediate are thread-local arrays with runtime indexing.
 #pragma once
 #include "core.cuh"
@@ -77,8 +76,7 @@ __device__ __forceinline__ void build_R_rt(double *R, int L, const double *Fs, d
     }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a, int la, int lb, int lc, int ld)
+static __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a, int la, int lb, int lc, int ld)
 {
     extern __shared__ double s_boys[];
     const int NA = ncart(la), NB = ncart(lb), NC = ncart(lc), ND = ncart(ld);
@@ -97,15 +95,12 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
         const int c = cd / ND, d = cd % ND;
         const int cx = cart_pow_rt(lc, c, 0), cy = cart_pow_rt(lc, c, 1), cz = cart_pow_rt(lc, c, 2);
         const int dx = cart_pow_rt(ld, d, 0), dy = cart_pow_rt(ld, d, 1), dz = cart_pow_rt(ld, d, 2);
-        uint2 ij = __ldg(a.list + (long long)e * a.list_step);
-        const int slice = (EPI == EPI_STORE) ? 0 : (int)(ij.x >> SLICE_SHIFT);
-        if (EPI != EPI_STORE) ij.x &= PAIR_MASK;
+        const uint2 ij = __ldg(a.list + (long long)e * a.list_step);
         const PairHdr bh = ld_hdr(a.braH + ij.x);
         const PairHdr kh = ld_hdr(a.ketH + ij.y);
         double out[36];
         for (int x = 0; x < NAB; ++x) out[x] = 0.0;
-        const int ib0 = (EPI == EPI_STORE) ? 0 : slice * BRA_SLICE;
-        const int ib1 = (EPI == EPI_STORE) ? bh.pnum : min(bh.pnum, ib0 + BRA_SLICE);
+        const int ib0 = 0, ib1 = bh.pnum;
         for (int ib = ib0; ib < ib1; ++ib) {
             const PrimPair b = ld_prim(a.braP + bh.poff + ib);
             ETabRT Eb;
@@ -126,7 +121,7 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
                 double Fs[KB_MAXL + 1];
                 boys_eval_rt(L, T, s_boys, Fs);
                 {
-                    double s = b.cc * k.cc * sqrt(b.p * k.p) * rs;      // PrimPair::cc carries 1/sqrt(p)
+                    double s = b.cc * k.cc * sqrt(b.p * k.p) * rs * (1.0 / SQRTPI_2);      // PrimPair::cc carries 1/sqrt(p) and sqrt(sqrt(pi)/2); boys_eval_rt returns the true F_m
                     const double m2a = -2.0 * alpha;
                     for (int nn = 0; nn <= L; ++nn) { Fs[nn] *= s; s *= m2a; }
                 }
@@ -162,74 +157,9 @@ __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const EriArgs a
             }
         }
         const double scd = comp_scale_rt(lc, c) * comp_scale_rt(ld, d);
-        if (EPI == EPI_STORE) {
-            double *o = a.out + e * (unsigned long long)(NAB * NCD);
-            for (int ab = 0; ab < NAB; ++ab)
-                o[ab * NCD + cd] = out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB));
-        } else {
-            const bool sameAB = (bh.shA == bh.shB), sameCD = (kh.shA == kh.shB);
-            const bool samePair = a.same_class && (ij.x == ij.y);
-            const int hiB = max(bh.bfA, bh.bfB), hiK = max(kh.bfA, kh.bfB);
-            // block digestion needs a real density and different leading shells; one-shell pairs keep the
-            // components a >= b (c >= d) with half weight on the diagonal (see digest_block in kernels_a.cuh)
-            const bool fast = (a.dg.dPim == nullptr) && !a.dg.fixed && (hiB != hiK);
-            const double wcd = !sameCD ? 1.0 : (c > d ? 1.0 : (c == d ? 0.5 : 0.0));
-            if (fast && wcd != 0.0) {
-                // shell-level digestion for this thread's (c,d): see digest_block in kernels_a.cuh
-                const DigestGeom g = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
-                const double *__restrict__ P = a.dg.dPre;
-                const double *__restrict__ SQ = a.dg.SQ;
-                double *__restrict__ G = a.dg.Gre;
-                const double tol = a.dg.tol;
-                const long long ocd = g.cd.base + c * g.cd.s0 + d * g.cd.s1;
-                const double pcd = __ldg(&P[ocd]), qcd = __ldg(&SQ[ocd]), pcd4 = 4.0 * fabs(pcd);
-                double Pbc[6], Pbd[6], Kbc[6], Kbd[6];
-                for (int b = 0; b < NB; ++b) {
-                    Pbc[b] = __ldg(&P[g.pbc.base + b * g.pbc.s0 + c * g.pbc.s1]);
-                    Pbd[b] = __ldg(&P[g.pbd.base + b * g.pbd.s0 + d * g.pbd.s1]);
-                    Kbc[b] = 0.0; Kbd[b] = 0.0;
-                }
-                double jcd = 0.0;
-                for (int aa = 0; aa < NA; ++aa) {
-                    const double pac = __ldg(&P[g.pac.base + aa * g.pac.s0 + c * g.pac.s1]);
-                    const double pad = __ldg(&P[g.pad.base + aa * g.pad.s0 + d * g.pad.s1]);
-                    double kac = 0.0, kad = 0.0;
-                    for (int b = 0; b < NB; ++b) {
-                        const int ab = aa * NB + b;
-                        const long long oab = g.ab.base + aa * g.ab.s0 + b * g.ab.s1;
-                        const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
-                        double dmax = fmax(4.0 * fabs(pab), pcd4);
-                        dmax = fmax(dmax, fmax(fmax(fabs(pac), fabs(pad)), fmax(fabs(Pbc[b]), fabs(Pbd[b]))));
-                        const double bound = (qab * qcd) * dmax;
-                        const double wab = !sameAB ? 1.0 : (aa > b ? 1.0 : (aa == b ? 0.5 : 0.0));
-                        const double sc = 8.0 * (wab * wcd) * scd * comp_scale_rt(la, aa) * comp_scale_rt(lb, b);
-                        const double e = (bound < tol) ? 0.0 : sc * out[ab];
-                        const double eq = -0.25 * e;
-                        red_add_f64(&G[oab], pcd * e);
-                        jcd = fma(pab, e, jcd);
-                        kac = fma(Pbd[b], eq, kac);
-                        Kbd[b] = fma(pac, eq, Kbd[b]);
-                        kad = fma(Pbc[b], eq, kad);
-                        Kbc[b] = fma(pad, eq, Kbc[b]);
-                    }
-                    red_add_f64(&G[g.gac.base + aa * g.gac.s0 + c * g.gac.s1], kac);
-                    red_add_f64(&G[g.gad.base + aa * g.gad.s0 + d * g.gad.s1], kad);
-                }
-                for (int b = 0; b < NB; ++b) {
-                    red_add_f64(&G[g.gbc.base + b * g.gbc.s0 + c * g.gbc.s1], Kbc[b]);
-                    red_add_f64(&G[g.gbd.base + b * g.gbd.s0 + d * g.gbd.s1], Kbd[b]);
-                }
-                red_add_f64(&G[ocd], jcd);
-            } else if (!fast) {
-                for (int ab = 0; ab < NAB; ++ab) {
-                    const double v = out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB));
-                    if (a.dg.fixed)
-                        digest_fn_quartet<true>(a.dg, bh.bfA + ab / NB, bh.bfB + ab % NB, kh.bfA + c, kh.bfB + d, sameAB, sameCD, samePair, v);
-                    else
-                        digest_fn_quartet<false>(a.dg, bh.bfA + ab / NB, bh.bfB + ab % NB, kh.bfA + c, kh.bfB + d, sameAB, sameCD, samePair, v);
-                }
-            }
-        }
+        double *o = a.out + e * (unsigned long long)(NAB * NCD);
+        for (int ab = 0; ab < NAB; ++ab)
+            o[ab * NCD + cd] = out[ab] * (scd * comp_scale_rt(la, ab / NB) * comp_scale_rt(lb, ab % NB));
     }
 }
 

@@ -71,6 +71,9 @@ static void boys_ref_ld(int mmax, long double T, long double *F)
     for (int m = mmax; m > 0; --m) F[m - 1] = (2.0L * T * F[m] + eT) / (2.0L * m - 1.0L);
 }
 
+// every entry carries 2/sqrt(pi): the pair coefficients carry sqrt(pi)/2 (see PrimPair::cc), so neither Boys branch of
+// the class kernels multiplies by it; boys_eval_rt (generic kernel, one-electron kernel, probes) undoes the factor
+static const long double INV_SQRTPI_2 = 1.0L / 0.886226925452758013649083741670572591L;
 static void make_boys_table(int L, std::vector<double> &tab)
 {
     tab.assign((size_t)BOYS_ROWS * BOYS_STRIDE, 0.0);
@@ -81,9 +84,9 @@ static void make_boys_table(int L, std::vector<double> &tab)
         long double fact = 1.0L;
         for (int k = 0; k <= 8; ++k) {
             if (k > 0) fact *= k;
-            tab[(size_t)r * BOYS_STRIDE + k] = (double)(F[L + k] / fact);
+            tab[(size_t)r * BOYS_STRIDE + k] = (double)(F[L + k] / fact * INV_SQRTPI_2);
         }
-        tab[(size_t)r * BOYS_STRIDE + 9] = (double)expl(-T0);
+        tab[(size_t)r * BOYS_STRIDE + 9] = (double)(expl(-T0) * INV_SQRTPI_2);
     }
 }
 
@@ -116,6 +119,8 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     cudaSetDevice(b->device);
     for (auto &p : b->pc) {
         cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.prim_soa_dev); cudaFree(p.prim_row_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
+        cudaFree(p.vhdr_dev); cudaFree(p.vsoa_dev); cudaFree(p.vrow_dev); cudaFree(p.vQs_dev); cudaFree(p.vQmax_dev); cudaFree(p.vK_dev);
+        cudaFree(p.vparent_dev); cudaFree(p.vslice_dev); cudaFree(p.vsh_dev); cudaFree(p.vgeo_dev); cudaFree(p.vpmin_dev); cudaFree(p.geo_dev); cudaFree(p.pmin_dev);
     }
     for (auto &t : b->boys_dev) cudaFree(t);
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
@@ -132,6 +137,132 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
 
 static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *am, const int *nprim, const int *prim_off,
                              const double *centre, const double *exps, const double *coefs, const int *bf0, double prim_cut);
+
+// bounding sphere (centre of the bounding box, largest distance to it) of n product centres, and their smallest exponent
+static void prim_bounds(const PrimPair *pp, int n, double4 *geo, double *pmin)
+{
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, pm = 1e300;
+    for (int k = 0; k < n; ++k) {
+        const double c[3] = {pp[k].Px, pp[k].Py, pp[k].Pz};
+        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], c[d]); hi[d] = std::max(hi[d], c[d]); }
+        pm = std::min(pm, pp[k].p);
+    }
+    const double cx = 0.5 * (lo[0] + hi[0]), cy = 0.5 * (lo[1] + hi[1]), cz = 0.5 * (lo[2] + hi[2]);
+    double r2 = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const double dx = pp[k].Px - cx, dy = pp[k].Py - cy, dz = pp[k].Pz - cz;
+        r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+    }
+    *geo = make_double4(cx, cy, cz, std::sqrt(r2) * (1.0 + 1e-12) + 1e-12);
+    *pmin = pm;
+}
+
+__global__ void qs_chunk_max_kernel(const double *Qs, int npairs, double *Qmax);
+
+// Virtual bra pairs of every class (see PairClass in handle.h).  Called whenever the Schwarz data change: the sort key
+// uses the Schwarz bound of the parent pair.  Host work: O(pairs log pairs) once per geometry.
+static int build_virtual_pairs(mmdb_basis *b)
+{
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (const ShellH &h : b->sh) {
+        const double c[3] = {h.x, h.y, h.z};
+        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], c[d]); hi[d] = std::max(hi[d], c[d]); }
+    }
+    double ext = 1e-6;
+    for (int d = 0; d < 3; ++d) ext = std::max(ext, hi[d] - lo[d]);
+    auto spread = [](unsigned v) {      // 10 bits -> every third bit
+        unsigned long long x = v & 0x3ffu;
+        x = (x | (x << 16)) & 0x30000ffull;
+        x = (x | (x << 8)) & 0x300f00full;
+        x = (x | (x << 4)) & 0x30c30c3ull;
+        x = (x | (x << 2)) & 0x9249249ull;
+        return x;
+    };
+    struct VP { int parent, slice, p0, pn; double qs; unsigned long long key; double4 geo; double pmin; };
+    for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
+        PairClass &P = b->pc[c];
+        if (P.npairs == 0) continue;
+        std::vector<double> Qs(P.npairs);
+        CU(cudaMemcpy(Qs.data(), P.Qs_dev, sizeof(double) * P.npairs, cudaMemcpyDeviceToHost));
+        std::vector<VP> v;
+        for (int i = 0; i < P.npairs; ++i) {
+            const PairHdr &h = P.hdr[i];
+            for (int p0 = 0, sl = 0; p0 < h.pnum; p0 += BRA_SLICE, ++sl) {
+                VP x;
+                x.parent = i; x.slice = sl; x.p0 = p0; x.pn = std::min(BRA_SLICE, h.pnum - p0); x.qs = Qs[i];
+                prim_bounds(&P.prim[h.poff + p0], x.pn, &x.geo, &x.pmin);
+                // key: primitive count (desc) | Schwarz half-decade (desc) | Morton code of the slice centre
+                int hd = 0;
+                if (x.qs > 0.0 && std::isfinite(x.qs)) hd = std::max(0, std::min(255, (int)std::floor(2.0 * std::log10(x.qs)) + 200));
+                const unsigned qx = (unsigned)(1023.0 * (x.geo.x - lo[0]) / ext), qy = (unsigned)(1023.0 * (x.geo.y - lo[1]) / ext),
+                               qz = (unsigned)(1023.0 * (x.geo.z - lo[2]) / ext);
+                const unsigned long long morton = spread(qx) | (spread(qy) << 1) | (spread(qz) << 2);
+                x.key = ((unsigned long long)(BRA_SLICE - x.pn) << 40) | ((unsigned long long)(255 - hd) << 32) | morton;
+                v.push_back(x);
+            }
+        }
+        std::stable_sort(v.begin(), v.end(), [](const VP &x, const VP &y) { return x.key < y.key; });
+        const int nvp = (int)v.size();
+        const long long nprim = (long long)P.prim.size();
+        std::vector<PairHdr> vh(nvp);
+        std::vector<double> vqs(nvp), vpm(nvp);
+        std::vector<int> vk(nvp), vpar(nvp), vsl(nvp);
+        std::vector<int2> vshl(nvp);
+        std::vector<double4> vg(nvp);
+        std::vector<long long> row(BRA_SLICE + 1, 0);
+        for (int k = 0; k < BRA_SLICE; ++k) {
+            long long nk = 0;
+            while (nk < nvp && v[nk].pn > k) ++nk;
+            row[k + 1] = row[k] + nk;
+        }
+        std::vector<double> soa((size_t)8 * nprim);
+        for (int i = 0; i < nvp; ++i) {
+            const VP &x = v[i];
+            PairHdr h = P.hdr[x.parent];
+            h.poff += x.p0; h.pnum = x.pn; h.pad0 = x.parent; h.pad1 = x.slice; h.Qs = x.qs;
+            vh[i] = h; vqs[i] = x.qs; vpm[i] = x.pmin; vk[i] = x.pn; vpar[i] = x.parent; vsl[i] = x.slice;
+            vshl[i] = make_int2(h.shA, h.shB); vg[i] = x.geo;
+            for (int k = 0; k < x.pn; ++k) {
+                const PrimPair &q = P.prim[h.poff + k];
+                const double f[8] = {q.Px, q.Py, q.Pz, q.p, q.cc, q.PAx, q.PAy, q.PAz};
+                for (int z = 0; z < 8; ++z) soa[(size_t)z * nprim + row[k] + i] = f[z];
+            }
+        }
+        if (P.nvp != nvp) {
+            cudaFree(P.vhdr_dev); cudaFree(P.vsoa_dev); cudaFree(P.vrow_dev); cudaFree(P.vQs_dev); cudaFree(P.vQmax_dev); cudaFree(P.vK_dev);
+            cudaFree(P.vparent_dev); cudaFree(P.vslice_dev); cudaFree(P.vsh_dev); cudaFree(P.vgeo_dev); cudaFree(P.vpmin_dev);
+            P.vhdr_dev = nullptr; P.vsoa_dev = nullptr; P.vrow_dev = nullptr; P.vQs_dev = nullptr; P.vQmax_dev = nullptr; P.vK_dev = nullptr;
+            P.vparent_dev = nullptr; P.vslice_dev = nullptr; P.vsh_dev = nullptr; P.vgeo_dev = nullptr; P.vpmin_dev = nullptr;
+            P.nvp = 0;
+            CU(cudaMalloc(&P.vhdr_dev, sizeof(PairHdr) * nvp));
+            CU(cudaMalloc(&P.vsoa_dev, sizeof(double) * soa.size()));
+            CU(cudaMalloc(&P.vrow_dev, sizeof(long long) * BRA_SLICE));
+            CU(cudaMalloc(&P.vQs_dev, sizeof(double) * nvp));
+            CU(cudaMalloc(&P.vQmax_dev, sizeof(double) * ((nvp + 255) / 256)));
+            CU(cudaMalloc(&P.vK_dev, sizeof(int) * nvp));
+            CU(cudaMalloc(&P.vparent_dev, sizeof(int) * nvp));
+            CU(cudaMalloc(&P.vslice_dev, sizeof(int) * nvp));
+            CU(cudaMalloc(&P.vsh_dev, sizeof(int2) * nvp));
+            CU(cudaMalloc(&P.vgeo_dev, sizeof(double4) * nvp));
+            CU(cudaMalloc(&P.vpmin_dev, sizeof(double) * nvp));
+            P.nvp = nvp;
+        }
+        CU(cudaMemcpy(P.vhdr_dev, vh.data(), sizeof(PairHdr) * nvp, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vsoa_dev, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vrow_dev, row.data(), sizeof(long long) * BRA_SLICE, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vQs_dev, vqs.data(), sizeof(double) * nvp, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vK_dev, vk.data(), sizeof(int) * nvp, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vparent_dev, vpar.data(), sizeof(int) * nvp, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vslice_dev, vsl.data(), sizeof(int) * nvp, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vsh_dev, vshl.data(), sizeof(int2) * nvp, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vgeo_dev, vg.data(), sizeof(double4) * nvp, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(P.vpmin_dev, vpm.data(), sizeof(double) * nvp, cudaMemcpyHostToDevice));
+        qs_chunk_max_kernel<<<((nvp + 255) / 256 + 3) / 4, 128>>>(P.vQs_dev, nvp, P.vQmax_dev);
+    }
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return MMDB_OK;
+}
 
 extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const int *nprim, const int *prim_off,
                                  const double *centre, const double *exps, const double *coefs, const int *bf0,
@@ -222,10 +353,15 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
                     q.Py = (ea * sa.y + eb * sb.y) / p;
                     q.Pz = (ea * sa.z + eb * sb.z) / p;
                     q.PAx = q.Px - sa.x; q.PAy = q.Py - sa.y; q.PAz = q.Pz - sa.z;
-                    q.cc = c2 * K * SQRT2_PI54 / (p * std::sqrt(p));    // divided by sqrt(p): see prim_R (core.cuh)
+                    // divided by sqrt(p): see prim_Fs (core.cuh); times sqrt(sqrt(pi)/2): a product of two carries the
+                    // sqrt(pi)/2 of the asymptotic Boys function
+                    q.cc = c2 * K * SQRT2_PI54 / (p * std::sqrt(p)) * std::sqrt(SQRTPI_2);
                     t.pp.push_back(q);
                 }
             if (t.pp.empty()) continue;
+            // tight primitive pairs first: the slices of a virtual bra pair then hold primitives of similar exponent, and
+            // the tight slices are far-field (asymptotic Boys branch) at almost any distance
+            std::stable_sort(t.pp.begin(), t.pp.end(), [](const PrimPair &x, const PrimPair &y) { return x.p > y.p; });
             t.h.pnum = (int)t.pp.size();
             tmp[pc_index(sa.am, sb.am)].push_back(std::move(t));
         }
@@ -237,16 +373,12 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         P.npairs = (int)v.size();
         for (auto &t : v) {
             t.h.poff = (int)P.prim.size();
+            t.h.pad0 = (int)P.hdr.size();        // own index in the class (virtual pairs carry their parent's here)
             P.prim.insert(P.prim.end(), t.pp.begin(), t.pp.end());
             P.hdr.push_back(t.h);
         }
         P.nprimpairs = (int64_t)P.prim.size();
-        P.slice_entries = 0;
-        for (auto &h : P.hdr) P.slice_entries += (size_t)((h.pnum + BRA_SLICE - 1) / BRA_SLICE);
         if (P.npairs == 0) continue;
-        if ((unsigned)P.npairs > PAIR_MASK) {
-            return fail(MMDB_ERR_UNSUPPORTED, "more than 2^24 shell pairs in one class");
-        }
         std::vector<int> K(P.npairs);
         std::vector<int2> shs(P.npairs);
         for (int i = 0; i < P.npairs; ++i) {
@@ -282,6 +414,16 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
             CU(cudaMalloc(&P.prim_row_dev, sizeof(long long) * kmax));
             CU(cudaMemcpy(P.prim_soa_dev, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice));
             CU(cudaMemcpy(P.prim_row_dev, row.data(), sizeof(long long) * kmax, cudaMemcpyHostToDevice));
+        }
+        {   // bounding sphere of the product centres and the smallest total exponent of every pair (ket side of the
+            // far-field test in the screening kernel)
+            std::vector<double4> geo(P.npairs);
+            std::vector<double> pmin(P.npairs);
+            for (int i = 0; i < P.npairs; ++i) prim_bounds(&P.prim[P.hdr[i].poff], P.hdr[i].pnum, &geo[i], &pmin[i]);
+            CU(cudaMalloc(&P.geo_dev, sizeof(double4) * P.npairs));
+            CU(cudaMalloc(&P.pmin_dev, sizeof(double) * P.npairs));
+            CU(cudaMemcpy(P.geo_dev, geo.data(), sizeof(double4) * P.npairs, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(P.pmin_dev, pmin.data(), sizeof(double) * P.npairs, cudaMemcpyHostToDevice));
         }
         CU(cudaMemset(P.Qs_dev, 0, sizeof(double) * P.npairs));
         CU(cudaMemcpy(P.K_dev, K.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
@@ -356,7 +498,7 @@ DECL(2, 1, 2, 1) DECL(2, 2, 1, 1) DECL(2, 2, 2, 0) DECL(2, 2, 2, 1) DECL(2, 2, 2
 // every class (ss|ss) ... (dd|dd) has a class-specialised kernel; the generic runtime-L kernel (impl = 1) is the
 // independent cross-check
 // (la lb) >= (lc ld) in pair-class order is required
-static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a, int epi, int impl, cudaStream_t st)
+static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a, int kind, int impl, cudaStream_t st)
 {
     const int L = la + lb + lc + ld;
     a.boys_tab = b->boys_dev[L];
@@ -367,7 +509,7 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
         switch (key) {
 #define CASE(LA, LB, LC, LD)                                  \
     case ((LA * 3 + LB) * 3 + LC) * 3 + LD:                   \
-        e = launch_class<LA, LB, LC, LD>(a, epi, gridA, st);  \
+        e = launch_class<LA, LB, LC, LD>(a, kind, gridA, st); \
         break;
             CASE(0, 0, 0, 0) CASE(1, 0, 0, 0) CASE(1, 0, 1, 0) CASE(1, 1, 0, 0) CASE(1, 1, 1, 0) CASE(1, 1, 1, 1)
             CASE(2, 0, 0, 0) CASE(2, 0, 1, 0) CASE(2, 0, 1, 1) CASE(2, 0, 2, 0)
@@ -379,12 +521,11 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
                 return fail(MMDB_ERR_INVALID, "launch_eri: class not instantiated");
         }
     } else {
+        // generic runtime-L kernel: the independent cross-check of the class kernels (stores integrals only)
+        if (kind != LK_STORE) return fail(MMDB_ERR_INVALID, "launch_eri: the generic kernel only stores integrals");
         const size_t smem = BOYS_ROWS * BOYS_STRIDE * sizeof(double);
         const int grid = b->nsm * 8;
-        if (epi == EPI_STORE)
-            eri_generic_kernel<EPI_STORE><<<grid, KB_THREADS, smem, st>>>(a, la, lb, lc, ld);
-        else   // the generic kernel decides block / per-function digestion per quartet, so it serves both lists
-            eri_generic_kernel<EPI_DIGEST><<<grid, KB_THREADS, smem, st>>>(a, la, lb, lc, ld);
+        eri_generic_kernel<<<grid, KB_THREADS, smem, st>>>(a, la, lb, lc, ld);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return fail(MMDB_ERR_CUDA, std::string("ERI kernel launch: ") + cudaGetErrorString(e));
@@ -460,30 +601,41 @@ __global__ void qs_chunk_max_kernel(const double *Qs, int npairs, double *Qmax)
     if (lane == 0) Qmax[chunk] = m;
 }
 
-// Shell-level screen -> compact quartet list.
-// Rows are KET pairs j in [row0,row1) (j % nshards == shard), columns are BRA pairs i (i >= j when the
-// two classes coincide).  One block handles one row x 1024 consecutive columns (two-phase, see the kernel),
-// block-wide prefix sum, ONE atomic per tile to reserve list space.  Entries of a row are written in
-// column order, so consecutive list entries share the ket pair (warp-uniform in the ERI kernels: the
-// inner primitive loop and the J_cd reduction run on broadcast data) and walk the bra pairs.
+// Shell-level screen -> compact quartet lists.
+// Rows are KET pairs j in [row0,row1) (j % nshards == shard), columns are BRA pairs i: for direct builds the class's
+// VIRTUAL bra pairs (slices of <= BRA_SLICE primitive pairs, sorted by primitive count / Schwarz half-decade / Morton
+// code), for the dense fill the shell pairs themselves.  When the two classes coincide only columns whose (parent) pair
+// index is >= j are candidates.  One block handles one row x 1024 consecutive columns (two-phase, see the kernel),
+// block-wide prefix sum, ONE atomic per list and tile to reserve space.  Entries of a row are written in column order,
+// so consecutive list entries share the ket pair (warp-uniform in the ERI kernels: the inner primitive loop and the
+// J_cd reduction run on broadcast data) and walk bra pairs of one contraction depth that are close in space.
+// Direct builds get THREE lists per class pair:
+//   far   block-digestible entries all of whose primitive quartets are on the asymptotic Boys branch
+//         (alpha_min d_min^2 >= T_max(L) from the bounding spheres of the two sets of product centres),
+//   near  the other block-digestible entries,
+//   slow  diagonal-type quartets / complex densities / deterministic mode (per-function digestion).
 struct ScreenArgs {
     const double *Qs_bra, *Qs_ket, *Qmax_bra;
     const int2 *sh_bra, *sh_ket;
     const int *K_bra, *K_ket;
+    const int *parent_bra;         // parent shell pair of a virtual bra pair (nullptr: columns are shell pairs)
+    const int *slice_bra;          // slice index of a virtual bra pair (0 = counts as the shell quartet) or nullptr
+    const double4 *geo_bra, *geo_ket;      // bounding spheres of the product centres (far-field test) or nullptr
+    const double *pmin_bra, *pmin_ket;     // smallest total exponents
+    double tmax;                   // T_max(L) of the class pair (+ margin)
     int nbra, row0, row1, same_class, shard, nshards, nshell, all_pass;
     int early;                     // warp-level early exit on the chunk maxima of the bra bounds
-    int split;                     // classify survivors: block-digestible entries front-to-back, the rest back-to-front
-    int force_slow;                // complex density: everything goes to the second list
+    int split;                     // direct build: classify survivors into the far / near / slow lists
+    int force_slow;                // complex density / deterministic mode: everything goes to the slow list
     const int *bf0;                // first function index per shell
-    long long cap;                 // list capacity (the slow list starts at list[cap-1] and grows downwards)
-    unsigned long long *count_slow;
-    unsigned long long *nquart;    // shell quartets (list entries count bra-primitive slices)
+    long long cap;                 // capacity of list_near (the slow list starts at list_near[cap-1] and grows downwards)
     const double *DS;
     const unsigned long long *dglob;
     double tol;
-    uint2 *list;
-    unsigned long long *count, *primq, *cand;
+    uint2 *list_far, *list_near;
+    unsigned long long *ctr;       // see CTR_* below
 };
+enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_PER_LAUNCH = 6 };
 
 constexpr int SCR_THREADS = 256;
 constexpr int SCR_CPT = 4;
@@ -494,7 +646,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
     __shared__ unsigned long long s_wcnt[SCR_THREADS / 32];
     __shared__ unsigned long long s_wk[SCR_THREADS / 32];
     __shared__ unsigned s_wcand[SCR_THREADS / 32];
-    __shared__ unsigned long long s_base, s_base_slow;
+    __shared__ unsigned long long s_base[3];
     __shared__ unsigned short s_slot[SCR_THREADS / 32][SCR_CPT * 32];    // compacted phase-1 survivors per warp
     const int ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(s.row1 - s.row0) * ntile;
@@ -505,21 +657,21 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const int j = s.row0 + (int)(blk / ntile);
         const int c0 = (int)(blk % ntile) * SCR_TILE;
         if (s.nshards > 1 && (j % s.nshards) != s.shard) continue;
-        const int cstart = s.same_class ? j : 0;
+        // columns are shell pairs in pair order (dense fill): the triangle i >= j is a column range
+        const int cstart = (s.same_class && s.parent_bra == nullptr) ? j : 0;
         if (c0 + SCR_TILE <= cstart) continue;
         const double qj = s.Qs_ket[j];
         if (!s.all_pass && s.early) {
             // dead tile (block-uniform test on the chunk maxima): nothing can pass, so skip the scans, barriers
-            // and atomics altogether — only the candidate count is kept for the statistics.  A tile is a
-            // latency chain of ~7 dependent memory round trips; most ket pairs of an extended system are weak
-            // and most of their tiles die here after one.
+            // and atomics altogether.  The columns are sorted by Schwarz half-decade inside a primitive-count group,
+            // so for a weak ket pair all but the leading chunks of every group die here after one load.
             bool tile_live = false;
             for (int ch = c0 >> 8; ch <= ((c0 + SCR_TILE - 1) >> 8); ++ch)
                 if (ch * 256 < s.nbra && !(s.Qmax_bra[ch] * qj * dg4 < s.tol)) tile_live = true;
             if (!tile_live) {
                 if (threadIdx.x == 0) {
                     const int lo = max(c0, cstart), hi = min(c0 + SCR_TILE, s.nbra);
-                    if (hi > lo) atomicAdd(s.cand, (unsigned long long)(hi - lo));
+                    if (hi > lo) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)(hi - lo));
                 }
                 continue;
             }
@@ -528,15 +680,16 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const unsigned long long kj = (unsigned long long)s.K_ket[j];
         // Two phases per warp (128 consecutive columns).  Phase 1: the cheap density-independent bound on
         // all columns, lane-strided (coalesced), survivors compacted into a per-warp slot array in column
-        // order.  Phase 2: the six-block density test, slicing and list classification run on the compacted
-        // survivors only, lane n taking survivors [n R, n R + R) — in extended systems ~10% of the columns
-        // pass phase 1, so the expensive part no longer runs with mostly idle lanes.
+        // order.  Phase 2: the six-block density test and list classification run on the compacted
+        // survivors only, lane n taking survivors [n R, n R + R).
         const int wbase = c0 + warp * (SCR_CPT * 32);
-        unsigned bits = 0, sbits = 0, ncand = 0, nent_fast = 0, nent_slow = 0;
-        unsigned nsl[SCR_CPT];
+        unsigned bits = 0, fbits = 0, sbits = 0, ncand = 0, nq = 0;
         int col[SCR_CPT];
         unsigned long long kk = 0;
         const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
+        double4 gk = make_double4(0.0, 0.0, 0.0, 0.0);
+        double qmin = 0.0;
+        if (s.split && s.geo_ket) { gk = s.geo_ket[j]; qmin = s.pmin_ket[j]; }
         // warp-level early exit: this warp's columns cannot pass if even their largest bound fails
         // (chunk maxima cover 256 consecutive pairs; a warp covers SCR_CPT * 32 of them)
         bool warp_live = s.all_pass || !s.early;
@@ -550,7 +703,8 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         for (int k = 0; k < SCR_CPT; ++k) {
             const int off = k * 32 + lane;
             const int i = wbase + off;
-            const bool cand = (i < s.nbra) && (i >= cstart);
+            bool cand = (i < s.nbra) && (i >= cstart);
+            if (cand && s.same_class && s.parent_bra != nullptr && warp_live) cand = s.parent_bra[i] >= j;
             ncand += cand ? 1u : 0u;            // candidates are counted for the statistics even when the warp exits early
             bool p1 = cand && warp_live;
             if (p1 && !s.all_pass) p1 = !(s.Qs_bra[i] * qj * dg4 < s.tol);
@@ -562,7 +716,6 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const unsigned per = (total + 31u) >> 5;      // survivors per lane (<= SCR_CPT)
 #pragma unroll
         for (int k = 0; k < SCR_CPT; ++k) {
-            nsl[k] = 0;
             col[k] = 0;
             const unsigned n = lane * per + k;
             if ((unsigned)k < per && n < total) {
@@ -582,20 +735,29 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                 }
                 if (pass) {
                     bits |= 1u << k;
-                    const int kb = s.K_bra[i];
-                    kk += (unsigned long long)kb * kj;
-                    // one list entry per slice of BRA_SLICE bra primitive pairs (direct builds only)
-                    nsl[k] = s.split ? (unsigned)((kb + BRA_SLICE - 1) / BRA_SLICE) : 1u;
-                    bool slow = false;
-                    if (s.split)   // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
-                        slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
-                    if (slow) { sbits |= 1u << k; nent_slow += nsl[k]; }
-                    else nent_fast += nsl[k];
+                    kk += (unsigned long long)s.K_bra[i] * kj;
+                    nq += (s.slice_bra == nullptr || s.slice_bra[i] == 0) ? 1u : 0u;
+                    if (s.split) {
+                        // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
+                        const bool slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
+                        if (slow) {
+                            sbits |= 1u << k;
+                        } else if (s.geo_bra) {
+                            // far field: every product centre of the bra slice lies in the sphere gb, every one of the ket
+                            // pair in gk, so |PQ| >= d for every primitive quartet; alpha >= pmin qmin / (pmin + qmin)
+                            const double4 gb = s.geo_bra[i];
+                            const double dx = gb.x - gk.x, dy = gb.y - gk.y, dz = gb.z - gk.z;
+                            const double d = sqrt(dx * dx + dy * dy + dz * dz) - gb.w - gk.w;
+                            const double pm = s.pmin_bra[i];
+                            if (d > 0.0 && (pm * qmin) * (d * d) >= s.tmax * (pm + qmin)) fbits |= 1u << k;
+                        }
+                    }
                 }
             }
         }
-        // block-wide exclusive scan of the survivor counts (fast list in the low half, slow list in the high half)
-        unsigned long long incl = (unsigned long long)nent_fast | ((unsigned long long)nent_slow << 32);
+        // block-wide exclusive scan of the survivor counts: far | near << 21 | slow << 42
+        const unsigned nfar = __popc(fbits), nslow = __popc(sbits), nnear = __popc(bits) - nfar - nslow;
+        unsigned long long incl = (unsigned long long)nfar | ((unsigned long long)nnear << 21) | ((unsigned long long)nslow << 42);
         const unsigned long long mine = incl;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -603,7 +765,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
             if (lane >= o) incl += v;
         }
         unsigned long long ks = kk;
-        unsigned cs = ncand | ((unsigned)__popc(bits) << 16);      // candidates | shell quartets (<= 8 each per thread)
+        unsigned cs = ncand | (nq << 16);      // candidates | shell quartets (<= SCR_CPT each per thread)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             ks += __shfl_xor_sync(0xffffffffu, ks, o);
@@ -623,26 +785,27 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                 tc += s_wcand[w] & 0xffffu;
                 tq += s_wcand[w] >> 16;
             }
-            if (tq) atomicAdd(s.nquart, (unsigned long long)tq);
-            const unsigned tf = (unsigned)(tot & 0xffffffffull), tsl = (unsigned)(tot >> 32);
-            s_base = tf ? atomicAdd(s.count, (unsigned long long)tf) : 0ull;
-            s_base_slow = tsl ? atomicAdd(s.count_slow, (unsigned long long)tsl) : 0ull;
-            if (tk) atomicAdd(s.primq, tk);
-            if (tc) atomicAdd(s.cand, (unsigned long long)tc);
+            if (tq) atomicAdd(s.ctr + CTR_NQUART, (unsigned long long)tq);
+            const unsigned tf = (unsigned)(tot & 0x1fffffull), tn = (unsigned)((tot >> 21) & 0x1fffffull), tsl = (unsigned)(tot >> 42);
+            s_base[0] = tf ? atomicAdd(s.ctr + CTR_FAR, (unsigned long long)tf) : 0ull;
+            s_base[1] = tn ? atomicAdd(s.ctr + CTR_NEAR, (unsigned long long)tn) : 0ull;
+            s_base[2] = tsl ? atomicAdd(s.ctr + CTR_SLOW, (unsigned long long)tsl) : 0ull;
+            if (tk) atomicAdd(s.ctr + CTR_PRIMQ, tk);
+            if (tc) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)tc);
         }
         __syncthreads();
         if (bits) {
             const unsigned long long excl = s_wcnt[warp] + (incl - mine);
-            long long pos = (long long)(s_base + (excl & 0xffffffffull));
-            long long spos = s.cap - 1 - (long long)(s_base_slow + (excl >> 32));
+            long long fpos = (long long)(s_base[0] + (excl & 0x1fffffull));
+            long long npos = (long long)(s_base[1] + ((excl >> 21) & 0x1fffffull));
+            long long spos = s.cap - 1 - (long long)(s_base[2] + (excl >> 42));
 #pragma unroll
             for (int k = 0; k < SCR_CPT; ++k)
                 if (bits & (1u << k)) {
-                    for (unsigned sl = 0; sl < nsl[k]; ++sl) {
-                        const uint2 ent = make_uint2((unsigned)col[k] | (sl << SLICE_SHIFT), (unsigned)j);
-                        if (sbits & (1u << k)) s.list[spos--] = ent;
-                        else s.list[pos++] = ent;
-                    }
+                    const uint2 ent = make_uint2((unsigned)col[k], (unsigned)j);
+                    if (sbits & (1u << k)) s.list_near[spos--] = ent;
+                    else if (fbits & (1u << k)) s.list_far[fpos++] = ent;
+                    else s.list_near[npos++] = ent;
                 }
         }
         __syncthreads();
@@ -710,7 +873,7 @@ extern "C" int mmdb_eri_shell_quartets(mmdb_basis *b, int pc_bra, int pc_ket, in
     a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
     a.list = b->list_dev; a.list_step = 1; a.count_dev = nullptr; a.n = (unsigned long long)n; a.out = out_dev;
     a.same_class = (pc_bra == pc_ket);
-    return launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, impl, st);
+    return launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_STORE, impl, st);
 }
 
 extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
@@ -732,33 +895,43 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
         std::memset(&a, 0, sizeof(a));
         a.braH = P.hdr_dev; a.braP = P.prim_dev; a.braS = P.prim_soa_dev; a.braRow = P.prim_row_dev; a.braN = P.nprimpairs; a.ketH = P.hdr_dev; a.ketP = P.prim_dev;
         a.list = b->list_dev; a.list_step = 1; a.n = (unsigned long long)P.npairs; a.out = b->scratch_dev; a.same_class = 1;
-        CHK(launch_eri(b, P.la, P.lb, P.la, P.lb, a, EPI_STORE, 0, st));
+        CHK(launch_eri(b, P.la, P.lb, P.la, P.lb, a, LK_STORE, 0, st));
         schwarz_extract_kernel<<<(P.npairs + 127) / 128, 128, 0, st>>>(P.hdr_dev, P.npairs, P.la, P.lb, b->scratch_dev,
                                                                        b->nbf, b->Q_dev, b->SQ_dev, P.Qs_dev);
         qs_chunk_max_kernel<<<((P.npairs + 255) / 256 + 3) / 4, 128, 0, st>>>(P.Qs_dev, P.npairs, P.Qmax_dev);
     }
     CU(cudaGetLastError());
     if (Q_dev) CU(cudaMemcpyAsync(Q_dev, b->Q_dev, N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));            // once per geometry: the virtual bra pairs are sorted by these bounds on the host
+    CHK(build_virtual_pairs(b));
     b->have_schwarz = true;
     return MMDB_OK;
 }
 
-constexpr int CTR_PER_LAUNCH = 5;   // entries (fast list), primitive quartets, candidates, entries (slow list), shell quartets
-
+// use_vp: columns are the bra class's virtual pairs (direct builds); otherwise its shell pairs (dense fill)
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
-                      bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, uint2 *list,
-                      cudaStream_t st)
+                      bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, uint2 *list_far,
+                      uint2 *list_near, bool use_vp, cudaStream_t st)
 {
     ScreenArgs s;
-    s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.Qmax_bra = B.Qmax_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
-    s.K_bra = B.K_dev; s.K_ket = K.K_dev;
-    s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
+    std::memset(&s, 0, sizeof(s));
+    if (use_vp) {
+        s.Qs_bra = B.vQs_dev; s.Qmax_bra = B.vQmax_dev; s.sh_bra = B.vsh_dev; s.K_bra = B.vK_dev; s.nbra = B.nvp;
+        s.parent_bra = B.vparent_dev; s.slice_bra = B.vslice_dev; s.geo_bra = B.vgeo_dev; s.pmin_bra = B.vpmin_dev;
+        s.geo_ket = K.geo_dev; s.pmin_ket = K.pmin_dev;
+    } else {
+        s.Qs_bra = B.Qs_dev; s.Qmax_bra = B.Qmax_dev; s.sh_bra = B.sh_dev; s.K_bra = B.K_dev; s.nbra = B.npairs;
+    }
+    s.Qs_ket = K.Qs_dev; s.sh_ket = K.sh_dev; s.K_ket = K.K_dev;
+    s.tmax = (double)boys_tmax_i(B.la + B.lb + K.la + K.lb) + 0.5;     // margin: rounding of the bounding-sphere distances
+    s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
     s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
-    s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list = list;
-    s.count = b->ctr_dev + CTR_PER_LAUNCH * slot; s.primq = s.count + 1; s.cand = s.count + 2; s.count_slow = s.count + 3; s.nquart = s.count + 4;
+    s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list_far = list_far; s.list_near = list_near;
+    s.ctr = b->ctr_dev + CTR_PER_LAUNCH * slot;
     s.early = getenv("MMDB_SCREEN_NO_EARLY_EXIT") ? 0 : 1;
     s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
-    const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
+    if (getenv("MMDB_NO_FAR_LIST")) { s.geo_bra = nullptr; }       // A/B switch: everything block-digestible goes to the near list
+    const long long ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(row1 - row0) * ntile;
     const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 32);
     if (grid > 0) screen_kernel<<<grid, SCR_THREADS, 0, st>>>(s);
@@ -792,13 +965,13 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
                 CHK(ensure_list(b, cap));
                 CHK(ensure_scratch(b, cap * nfn));
                 if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
-                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, b->list_dev, st));
+                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, b->list_dev, b->list_dev, false, st));
                 EriArgs a;
                 std::memset(&a, 0, sizeof(a));
                 a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
                 a.list = b->list_dev; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.out = b->scratch_dev;
                 a.same_class = (cb == ck);
-                CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_STORE, 0, st));
+                CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_STORE, 0, st));
                 scatter_dense_kernel<<<b->nsm * 16, 256, 0, st>>>(b->list_dev, b->ctr_dev + CTR_PER_LAUNCH * slot, B.hdr_dev, K.hdr_dev,
                                                                   B.la, B.lb, K.la, K.lb, cb == ck ? 1 : 0, b->scratch_dev, (int)N, TwoE_dev);
                 ++slot;
@@ -843,11 +1016,11 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
             // rows of this shard only count towards the list capacity
-            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.slice_entries * (size_t)nshards);
+            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.nvp * (size_t)nshards);
             const bool small = !timing && (size_t)B.npairs * K.npairs / nshards <= AUX_MAX_CANDIDATES;
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.slice_entries;   // room for every slice
+                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.nvp;   // room for every virtual pair
                 tasks.push_back(Task{cb, ck, row0, row1, cap, small});
                 (small ? cap_aux : cap_main) = std::max(small ? cap_aux : cap_main, cap);
             }
@@ -856,9 +1029,11 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     // stream while the ERI kernels of task m execute (it fills the SMs the persistent ERI grid vacates at its tail
     // instead of serialising behind it).  Per-class event timing keeps everything on one stream.
     const bool pipeline = !timing;
-    CHK(ensure_list(b, (pipeline ? 2 : 1) * cap_main + cap_aux));          // [main 0 | main 1 | aux] regions of one buffer
-    uint2 *list_main[2] = {b->list_dev, b->list_dev + (pipeline ? cap_main : 0)};
-    uint2 *list_aux = b->list_dev + (pipeline ? 2 : 1) * cap_main;
+    // every region holds a far list [cap] followed by a near list [cap] (whose tail end is the slow list)
+    CHK(ensure_list(b, 2 * ((pipeline ? 2 : 1) * cap_main + cap_aux)));    // [main 0 | main 1 | aux] regions of one buffer
+    uint2 *list_main[2] = {b->list_dev, b->list_dev + (pipeline ? 2 * cap_main : 0)};
+    uint2 *list_aux = b->list_dev + (pipeline ? 2 : 1) * 2 * cap_main;
+    const size_t cap_region[2] = {cap_main, cap_aux};
     if ((int)tasks.size() * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
     cudaStream_t sa = st;
     if (cap_aux > 0) {
@@ -912,9 +1087,10 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                 CU(cudaEventCreate(&ln.e1));
                 CU(cudaEventRecord(ln.e0, s1));
             }
+            uint2 *list_far = list, *list_near = list + cap_region[t.aux ? 1 : 0];
             CHK(run_screen(b, B, K, t.cb == t.ck, t.row0, t.row1, shard, nshards, false, tol, slot, true,
                            dP_im_dev != nullptr || (flags & 2) != 0,
-                           (long long)t.cap, list, s_scr));
+                           (long long)t.cap, list_far, list_near, true, s_scr));
             if (piped) {
                 CU(cudaEventRecord(ev_ready, ss));
                 CU(cudaStreamWaitEvent(st, ev_ready, 0));
@@ -922,15 +1098,20 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             if (timing) CU(cudaEventRecord(ln.em, s1));
             EriArgs a;
             std::memset(&a, 0, sizeof(a));
-            a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
-            a.list = list; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot; a.same_class = (t.cb == t.ck);
+            // bra side = the class's virtual pairs (slices of <= BRA_SLICE primitive pairs)
+            a.braH = B.vhdr_dev; a.braP = B.prim_dev; a.braS = B.vsoa_dev; a.braRow = B.vrow_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+            a.same_class = (t.cb == t.ck);
             a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
             a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
             a.dg.fixed = (flags & 2) ? 1 : 0;
-            // block-digestible quartets, then the second list (diagonal-type quartets / complex density)
-            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST, 0, s1));
-            a.list = list + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + 3;
-            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, EPI_DIGEST_SLOW, 0, s1));
+            // far-field list (asymptotic Boys branch only), near list, then the slow list (diagonal-type quartets /
+            // complex density / deterministic mode)
+            a.list = list_far; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_FAR;
+            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST_FAR, 0, s1));
+            a.list = list_near; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_NEAR;
+            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST, 0, s1));
+            a.list = list_near + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_SLOW;
+            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST_SLOW, 0, s1));
             if (piped) {
                 CU(cudaEventRecord(ev_done, st));
                 ++m_main;
@@ -948,14 +1129,16 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         CU(cudaMemcpyAsync(ctr.data(), b->ctr_dev, sizeof(unsigned long long) * CTR_PER_LAUNCH * slot, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof(*stats));
-        stats->launches = 2 + 3 * (int64_t)launches.size();
+        stats->launches = 2 + 4 * (int64_t)launches.size();
         for (auto &ln : launches) {
             const PairClass &B = b->pc[ln.cb], &K = b->pc[ln.ck];
-            const int64_t nq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 4];
-            const int64_t npq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 1];
-            stats->slow_quartets += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 3];
+            const int64_t nq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_NQUART];
+            const int64_t npq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_PRIMQ];
+            stats->slow_quartets += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_SLOW];
+            stats->far_entries += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_FAR];
+            stats->near_entries += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_NEAR];
             const int64_t nfn = (int64_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
-            stats->candidates += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + 2];
+            stats->candidates += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_CAND];
             stats->quartets += nq;
             stats->prim_quartets += npq;
             stats->fn_quartets += nq * nfn;
@@ -1049,6 +1232,7 @@ extern "C" int mmdb_set_schwarz_host(mmdb_basis *b, const double *Q_tri)
     }
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
+    CHK(build_virtual_pairs(b));
     b->have_schwarz = true;
     return MMDB_OK;
 }
@@ -1177,7 +1361,7 @@ __global__ void boys_class_probe_kernel(int64_t n, const double *T, const double
         prim_Fs<L>(Fs, 2.0, 2.0, 1.0, 1.0, T[i], s_boys);
         double sc = 1.0;
 #pragma unroll
-        for (int m = 0; m <= L; ++m) { out[i * (L + 1) + m] = Fs[m] * sc; sc *= -0.5; }
+        for (int m = 0; m <= L; ++m) { out[i * (L + 1) + m] = Fs[m] * sc * SQRTPI_2; sc *= -0.5; }      // unit coefficients carry no sqrt(pi)/2
     }
 }
 

@@ -182,6 +182,83 @@ def test_host_buffer_c_abi_entry_points(oracle, golden):
     assert rc != 0 and b"pc_bra" in lib.mmdb_last_error()
 
 
+def test_c_abi_communicator_and_allreduce():
+    """mmdb_comm_unique_id / mmdb_comm_init / mmdb_allreduce_G / mmdb_comm_destroy (NCCL behind the C ABI).  With one
+    visible GPU this is the single-rank communicator (the reduction is the identity); with two or more, two ranks run
+    in two threads of this process, each builds its shard of an H2O/cc-pVDZ Fock matrix and the all-reduced sum must
+    equal the unsharded build on both ranks."""
+    import ctypes as C
+    import threading
+    import torch
+    from mmd._b200 import lib as L
+    lib = L.load()
+    uid = (C.c_ubyte * 128)()
+    L.check(lib.mmdb_comm_unique_id(uid))
+    ndev = torch.cuda.device_count()
+    mol = Molecule(*synth.config("h2o_ccpvdz"))
+    N = mol.nbasis
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((N, N))
+    P = np.ascontiguousarray(0.1 * (A + A.T))
+    eng = mol.engine
+    eng.schwarz()
+    full = eng.formPT(P.astype(complex), np.zeros((N, N), dtype=complex), tol=1e-12).real
+    nranks = 2 if ndev >= 2 else 1
+    results, errors = [None] * nranks, []
+
+    def rank_main(r):
+        try:
+            with torch.cuda.device(r):
+                e = eng if r == 0 else E.Engine(mol.bfs, device=r)
+                if r != 0:
+                    e.schwarz()
+                comm = C.c_void_p()
+                L.check(lib.mmdb_comm_init(r, nranks, r, uid, C.byref(comm)))
+                dP = torch.from_numpy(P).to(e.tdev)
+                G = torch.zeros((N, N), dtype=torch.float64, device=e.tdev)
+                st = C.c_void_p(torch.cuda.current_stream(e.tdev).cuda_stream)
+                L.check(lib.mmdb_fock_direct(e.h, L.ptr(dP), None, 1e-12, L.ptr(G), None, r, nranks, 0, None, st))
+                L.check(lib.mmdb_allreduce_G(comm, L.ptr(G), G.numel(), 0, st))
+                torch.cuda.synchronize(e.tdev)
+                results[r] = G.cpu().numpy()
+                L.check(lib.mmdb_comm_destroy(comm))
+        except Exception as exc:      # surfaced in the main thread
+            errors.append(exc)
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for r in range(nranks):
+        assert np.abs(results[r] - full).max() < FOCK_TOL
+
+
+def test_far_and_near_lists_partition_the_work():
+    """The screening kernel sorts block-digestible entries into a far-field list (every primitive quartet on the
+    asymptotic Boys branch, proved from bounding spheres) and a near list.  Same G with the far list switched off,
+    and at benchmark-like separation most entries are far."""
+    import os
+    mol = Molecule(*synth.config("w8_ccpvdz"))
+    N = mol.nbasis
+    P = closed_form_densities(mol.bfs)["A"].astype(complex)
+    eng = mol.engine
+    scr = eng.schwarz()
+    G1 = eng.formPT(P, np.zeros_like(P), screen=scr, tol=1e-12)
+    st = dict(eng.last_stats)
+    assert st["far_entries"] > 0 and st["near_entries"] > 0
+    os.environ["MMDB_NO_FAR_LIST"] = "1"
+    try:
+        G2 = eng.formPT(P, np.zeros_like(P), screen=scr, tol=1e-12)
+        st2 = dict(eng.last_stats)
+    finally:
+        del os.environ["MMDB_NO_FAR_LIST"]
+    assert st2["far_entries"] == 0 and st2["near_entries"] == st["far_entries"] + st["near_entries"]
+    assert st2["quartets"] == st["quartets"] and st2["prim_quartets"] == st["prim_quartets"]
+    assert np.abs(G1 - G2).max() < FOCK_TOL
+
+
 def test_jk_incore_even_and_odd_sizes(oracle):
     rng = np.random.default_rng(2)
     he2 = "\n0 1\nHe 0.0 0.0 0.0\nHe 0.0 0.0 3.0\n"
