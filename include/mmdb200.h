@@ -164,6 +164,16 @@ int mmdb_eri_dense_host(mmdb_basis *b, double *TwoE_host);
 int mmdb_onee_host(mmdb_basis *b, int natom, const double *Z, const double *xyz, const double *origin,
                    double *S, double *T, double *V, double *M, double *L);
 
+/* ---- nuclear gradient (cython/grad.pyx + mmd/forces.py of the reference) ------------------------
+ * dE/dX of the closed-shell RHF energy, [natom][3] each (host): one-electron part (kinetic, nuclear attraction incl. the
+ * Hellmann-Feynman operator term, overlap x energy-weighted density), two-electron part (derivative ERIs contracted with
+ * the two-particle density 16 P_ij P_kl - 4 P_ik P_jl - 4 P_il P_jk as they are produced — no derivative tensor), and
+ * nuclear repulsion.  P = C_occ C_occ^T (no factor 2) and W = P F P: real (N,N) host matrices in device function order;
+ * shell_atom[s] = atom index of shell s.  Forces are minus the sum of the three parts.  d shells use f-type shifted
+ * primitives inside the kernels.  mmdb_schwarz must have been called. */
+int mmdb_gradient_host(mmdb_basis *b, int natom, const double *Z, const double *xyz, const int *shell_atom,
+                       const double *P, const double *W, double *grad_1e, double *grad_2e, double *grad_nuc);
+
 /* ---- post-SCF consumers of the dense tensor (next row) ------------------- */
 /* AO->MO transformation (mmd/postscf.py:21-41) by four cuBLAS DGEMM quarter transformations and the
  * closed-shell MP2 correlation energy (mmd/postscf.py:59-70).  Row-major (N,N,N,N) tensors; C_dev (N,N)

@@ -478,19 +478,26 @@ __host__ __device__ constexpr bool ket_uses_R(int KT, int KU, int KV)
 // One contracted shell quartet, ket component pairs [CD0, CD0+NCDC), class-specialised.
 // out[ab*NCDC + cdi] accumulates (ab|cd) WITHOUT the per-component normalisation.
 // ------------------------------------------------------------------------------------------
-template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SERIAL_CHUNKS, bool FAR = false>
+// SCR_OUT: the contracted block is accumulated in a global scratch column of the thread (element x at outg[x * ostride],
+// L2-resident, touched once per bra primitive pair) instead of registers — classes whose Hermite intermediate G already
+// fills the register file (dp bra pairs: 20 x 3 doubles) keep three ket component pairs per thread that way instead of
+// one, so Boys + R + the bra E table are built a third as often and the digestion shares its bra-block loads.
+template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SERIAL_CHUNKS, bool FAR = false, bool SCR_OUT = false>
 __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraSrc &bsrc,
                                                    const PairHdr &kh, const PrimPair *__restrict__ kp,
                                                    const double *__restrict__ boys_tab, double *r_smem, int r_stride,
-                                                   int ib0, int ib1, double (&out)[ncart(LA) * ncart(LB) * NCDC])
+                                                   int ib0, int ib1, double (&out)[ncart(LA) * ncart(LB) * NCDC],
+                                                   double *__restrict__ outg = nullptr, long long ostride = 0)
 {
     constexpr int LBRA = LA + LB, LKET = LC + LD, L = LBRA + LKET;
     constexpr int NA = ncart(LA), NB = ncart(LB), ND = ncart(LD);
     constexpr int NAB = NA * NB;
     constexpr int NHB = nherm(LBRA);
 
+    if constexpr (!SCR_OUT) {
 #pragma unroll
-    for (int x = 0; x < NAB * NCDC; ++x) out[x] = 0.0;
+        for (int x = 0; x < NAB * NCDC; ++x) out[x] = 0.0;
+    }
 
     for (int ib = ib0; ib < ib1; ++ib) {       // [ib0,ib1): this entry's slice of the bra primitive pairs
         const PrimPair b = ld_prim_soa(bsrc, ib);
@@ -687,6 +694,11 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
             constexpr int a = ab / NB, bb = ab % NB;
             constexpr int ax = cart_pow(LA, a, 0), ay = cart_pow(LA, a, 1), az = cart_pow(LA, a, 2);
             constexpr int bx = cart_pow(LB, bb, 0), by = cart_pow(LB, bb, 1), bz = cart_pow(LB, bb, 2);
+            double acc[NCDC];
+            if constexpr (SCR_OUT) {
+#pragma unroll
+                for (int cdi = 0; cdi < NCDC; ++cdi) acc[cdi] = 0.0;
+            }
             sfor<0, ax + bx + 1>([&](auto TT) {
                 constexpr int t = decltype(TT)::value;
                 sfor<0, ay + by + 1>([&](auto UU) {
@@ -696,11 +708,20 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                         constexpr int v = decltype(VV)::value;
                         const double coef = exy * Eb.v[2][az][bz][v];
 #pragma unroll
-                        for (int cdi = 0; cdi < NCDC; ++cdi)
-                            out[ab * NCDC + cdi] = fma(coef, G[hidx(t, u, v) * NCDC + cdi], out[ab * NCDC + cdi]);
+                        for (int cdi = 0; cdi < NCDC; ++cdi) {
+                            if constexpr (SCR_OUT) acc[cdi] = fma(coef, G[hidx(t, u, v) * NCDC + cdi], acc[cdi]);
+                            else out[ab * NCDC + cdi] = fma(coef, G[hidx(t, u, v) * NCDC + cdi], out[ab * NCDC + cdi]);
+                        }
                     });
                 });
             });
+            if constexpr (SCR_OUT) {
+#pragma unroll
+                for (int cdi = 0; cdi < NCDC; ++cdi) {
+                    double *o = outg + (long long)(ab * NCDC + cdi) * ostride;
+                    *o = (ib == ib0) ? acc[cdi] : (*o + acc[cdi]);
+                }
+            }
         });
     }
 }
@@ -781,6 +802,7 @@ struct EriArgs {
     unsigned long long n;
     const double *boys_tab;       // [BOYS_ROWS][BOYS_STRIDE] for this class's L (global)
     double *out;                  // EPI_STORE: [entry][nfn]
+    double *scratch;              // per-thread columns of the contracted block (classes with scratch_out): [x][grid threads]
     int same_class;               // bra class == ket class (entries with .x == .y are diagonal quartets)
     DigestArgs dg;                // EPI_DIGEST
 };
@@ -794,6 +816,8 @@ enum { EPI_STORE = 0, EPI_DIGEST = 1, EPI_DIGEST_SLOW = 2 };
 // quartets) are thereby spread over up to 8 threads; J/K digestion is linear in the integrals, so every slice
 // digests its own partial block.  Bounds the longest serial thread (the tail of every launch).
 constexpr int BRA_SLICE = 8;
+// padding entry of the compact quartet lists (the screening kernel flushes blocks of exactly 32 entries): skipped by the consumers
+constexpr unsigned LIST_NULL = 0xffffffffu;
 constexpr unsigned SLICE_SHIFT = 24;
 constexpr unsigned PAIR_MASK = (1u << SLICE_SHIFT) - 1u;
 

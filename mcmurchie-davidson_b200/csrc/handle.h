@@ -56,6 +56,7 @@ struct PairClass {
     std::vector<mmdb::PrimPair> prim;
     mmdb::PairHdr *hdr_dev = nullptr;
     mmdb::PrimPair *prim_dev = nullptr;
+    double2 *prim_ab_dev = nullptr;      // [nprimpairs] the two individual exponents of every primitive pair (gradient kernels)
     double *prim_soa_dev = nullptr;      // [8 fields][nprimpairs]: field f of primitive k of pair i at f*nprimpairs + row[k] + i
     long long *prim_row_dev = nullptr;   // [max pnum] row offsets of the structure-of-arrays copy
     double *Qs_dev = nullptr;   // [npairs]
@@ -89,6 +90,7 @@ struct mmdb_basis {
     std::vector<cudaEvent_t> ev_pool;             // per-task "list ready" / "list consumed" events of the screening pipeline
     double *scratch_dev = nullptr;
     size_t scratch_cap = 0;   // doubles
+    double *eri_scratch_dev = nullptr;            // [2 regions][54 * nsm * 2048] contracted-block columns of the scratch_out classes (main / aux stream)
     double *stage_host = nullptr, *stage_dev = nullptr;   // mmdb_formPT_host staging: 4 planes of N^2 doubles each (page-locked / device)
     size_t stage_n = 0;
 };

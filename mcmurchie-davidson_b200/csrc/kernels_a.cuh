@@ -19,11 +19,19 @@ __host__ __device__ constexpr int etab_size(int la, int lb)
     return n;
 }
 
+// Classes that keep the contracted block in a global scratch column (see eval_quartet_chunk, SCR_OUT): dp bra pairs
+// with a ket of at least three component pairs.  G (20 Hermite rows x 3 ket component pairs) fills the registers.
+template <int LA, int LB, int LC, int LD>
+__host__ __device__ constexpr bool scratch_out()
+{
+    return LA == 2 && LB == 1 && ncart(LC) * ncart(LD) >= 3;
+}
+
 // R_tuv lives in shared memory (one column per thread) for the high-L classes, in registers otherwise
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr bool r_in_smem()
 {
-    return LA + LB + LC + LD >= 5;
+    return LA + LB + LC + LD >= 5 || scratch_out<LA, LB, LC, LD>();
 }
 
 // ket component pairs per chunk
@@ -32,6 +40,7 @@ __host__ __device__ constexpr int chunk_ncd()
 {
     constexpr int NAB = ncart(LA) * ncart(LB), NCD = ncart(LC) * ncart(LD), NHB = nherm(LA + LB);
     int best = 1;
+    if (scratch_out<LA, LB, LC, LD>()) return 3;
     if (r_in_smem<LA, LB, LC, LD>()) {
         // live doubles: ket transform G + ket E table; bra transform G + out + bra E table
         constexpr int nEb = 3 * etab_size(LA, LB), nEk = 3 * etab_size(LC, LD);
@@ -280,7 +289,7 @@ __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestG
 // unrolled digestion was the bulk of the instruction footprint (ncu: stall_no_instruction dominant).
 template <int LA, int LB, int LC, int LD>
 __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB, int bfC, int bfD, int c, int d, double scd,
-                                          bool active, bool ket_uniform, const double *__restrict__ out)
+                                          bool active, bool ket_uniform, const double *__restrict__ out, long long ostride)
 {
     constexpr int NA = ncart(LA), NB = ncart(LB);
     const DigestGeom g = make_geom(dg.N, bfA, bfB, bfC, bfD);
@@ -322,7 +331,7 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
                 if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
                 const double dmax = fmax(4.0 * fabs(pab), fmax(ma, Mb[b]));
                 const double bound = (qab * qcd) * dmax;
-                const double e = (bound < tol) ? 0.0 : (s8 * wab * scd) * out[a * NB + b];
+                const double e = (bound < tol) ? 0.0 : (s8 * wab * scd) * out[(long long)(a * NB + b) * ostride];
                 const double eq = -0.25 * e;
                 red_add_f64(&G[oab], pcd * e);
                 jcd = fma(pab, e, jcd);
@@ -377,11 +386,49 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND;
     double out[NAB * NCDC];
+    constexpr bool SCR = scratch_out<LA, LB, LC, LD>();
+    // scratch column of this thread: element x at scr[x * sstride] (coalesced across the threads of the grid)
+    const long long sstride = (long long)gridDim.x * blockDim.x;
+    double *scr = SCR ? a.scratch + ((long long)blockIdx.x * blockDim.x + threadIdx.x) : nullptr;
     if (valid)
-        eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS, FAR>(
+        eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS, FAR, SCR>(
             bh, BraSrc{a.braS, a.braRow, a.braN, ibra}, kh, a.ketP, boys_tab,
             const_cast<double *>(boys_tab) + (FAR ? 0 : boys_rows(LA + LB + LC + LD) * BOYS_STRIDE) + threadIdx.x,
-            ka_threads<LA, LB, LC, LD, FAR>(), ib0, ib1, out);
+            ka_threads<LA, LB, LC, LD, FAR>(), ib0, ib1, out, scr, sstride);
+    if constexpr (SCR) {
+        if constexpr (EPI == EPI_STORE) {
+            if (valid) {
+                double *o = a.out + e * (unsigned long long)(NAB * NCD);
+                sfor<0, NAB>([&](auto ABI) {
+                    constexpr int ab = decltype(ABI)::value;
+                    constexpr double sab = comp_scale(LA, ab / NB) * comp_scale(LB, ab % NB);
+                    sfor<0, NCDC>([&](auto CDI) {
+                        constexpr int cdi = decltype(CDI)::value;
+                        constexpr int cd = CD0 + cdi;
+                        constexpr double sc = sab * comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND);
+                        o[ab * NCD + cd] = scr[(long long)(ab * NCDC + cdi) * sstride] * sc;
+                    });
+                });
+            }
+        } else if constexpr (EPI == EPI_DIGEST) {
+            sfor<0, NCDC>([&](auto CDI) {
+                constexpr int cdi = decltype(CDI)::value;
+                constexpr int cd = CD0 + cdi;
+                digest_cd_rt<LA, LB, LC, LD>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, cd / ND, cd % ND,
+                                             comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND), valid, ket_uniform,
+                                             scr + (long long)cdi * sstride, (long long)NCDC * sstride);
+            });
+        } else {
+            if (valid) {
+                double tmp[NAB * NCDC];
+#pragma unroll 1
+                for (int x = 0; x < NAB * NCDC; ++x) tmp[x] = scr[(long long)x * sstride];
+                if (a.dg.fixed) digest_block_slow<true>(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
+                else digest_block_slow<false>(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
+            }
+        }
+        return;
+    }
     if constexpr (EPI == EPI_STORE) {
         if (valid) {
             double *o = a.out + e * (unsigned long long)(NAB * NCD);
@@ -407,7 +454,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
 #pragma unroll
                 for (int x = 0; x < NAB; ++x) tmp[x] = out[x * NCDC + cdi];
                 digest_cd_rt<LA, LB, LC, LD>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, cd / ND, cd % ND,
-                                             comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND), valid, ket_uniform, tmp);
+                                             comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND), valid, ket_uniform, tmp, 1);
             });
         } else {
             const DigestGeom geom = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
@@ -468,8 +515,9 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD, FAR>(), min_blocks<
         for (; base < n; base += wstride) {
             if constexpr (LOCKSTEP) __syncthreads();
             const unsigned long long e = base + threadIdx.x;
-            const bool valid = e < n;
-            const uint2 ij = ij_next;
+            uint2 ij = ij_next;
+            const bool valid = (e < n) && (ij.x != LIST_NULL);       // LIST_NULL: padding of a screening flush block
+            if (ij.x == LIST_NULL) ij.x = 0u;
             // direct builds: ij.x indexes the class's VIRTUAL bra pairs (one slice of <= BRA_SLICE primitive pairs of a
             // shell pair, lib.cu build_virtual_pairs), whose header carries the slice's own primitive range
             const PairHdr bh = ld_hdr(a.braH + ij.x);

@@ -74,10 +74,12 @@ static void boys_ref_ld(int mmax, long double T, long double *F)
 // every entry carries 2/sqrt(pi): the pair coefficients carry sqrt(pi)/2 (see PrimPair::cc), so neither Boys branch of
 // the class kernels multiplies by it; boys_eval_rt (generic kernel, one-electron kernel, probes) undoes the factor
 static const long double INV_SQRTPI_2 = 1.0L / 0.886226925452758013649083741670572591L;
+static void make_boys_table(int L, std::vector<double> &tab);
+void mmdb_make_boys_table(int L, std::vector<double> &tab) { make_boys_table(L, tab); }     // grad.cu (orders up to 9)
 static void make_boys_table(int L, std::vector<double> &tab)
 {
     tab.assign((size_t)BOYS_ROWS * BOYS_STRIDE, 0.0);
-    long double F[BOYS_MAXL + 9 + 1];
+    long double F[BOYS_MAXL + 1 + 9 + 1];
     for (int r = 0; r < BOYS_ROWS; ++r) {
         const long double T0 = (long double)r * 0.125L;
         boys_ref_ld(L + 8, T0, F);
@@ -102,6 +104,16 @@ static int ensure_list(mmdb_basis *b, size_t entries)
     b->list_cap = entries;
     return MMDB_OK;
 }
+// scratch columns of the classes that keep their contracted block in global memory (kernels_a.cuh scratch_out):
+// 18 x 3 doubles per resident thread, one region per stream that can run class kernels concurrently
+static size_t eri_scratch_region(const mmdb_basis *b) { return (size_t)54 * b->nsm * 2048; }
+static int ensure_eri_scratch(mmdb_basis *b)
+{
+    if (b->eri_scratch_dev) return MMDB_OK;
+    CU(cudaMalloc(&b->eri_scratch_dev, 2 * eri_scratch_region(b) * sizeof(double)));
+    return MMDB_OK;
+}
+
 static int ensure_scratch(mmdb_basis *b, size_t doubles)
 {
     if (doubles <= b->scratch_cap) return MMDB_OK;
@@ -118,14 +130,14 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     if (!b) return MMDB_OK;
     cudaSetDevice(b->device);
     for (auto &p : b->pc) {
-        cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.prim_soa_dev); cudaFree(p.prim_row_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
+        cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.prim_ab_dev); cudaFree(p.prim_soa_dev); cudaFree(p.prim_row_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
         cudaFree(p.vhdr_dev); cudaFree(p.vsoa_dev); cudaFree(p.vrow_dev); cudaFree(p.vQs_dev); cudaFree(p.vQmax_dev); cudaFree(p.vK_dev);
         cudaFree(p.vparent_dev); cudaFree(p.vslice_dev); cudaFree(p.vsh_dev); cudaFree(p.vgeo_dev); cudaFree(p.vpmin_dev); cudaFree(p.geo_dev); cudaFree(p.pmin_dev);
     }
     for (auto &t : b->boys_dev) cudaFree(t);
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
     cudaFree(b->Dabs_dev); cudaFree(b->DS_dev); cudaFree(b->dglob_dev); cudaFree(b->list_dev);
-    cudaFree(b->ctr_dev); cudaFree(b->scratch_dev);
+    cudaFree(b->ctr_dev); cudaFree(b->scratch_dev); cudaFree(b->eri_scratch_dev);
     if (b->stage_host) cudaFreeHost(b->stage_host);
     cudaFree(b->stage_dev);
     if (b->aux_stream) { cudaStreamDestroy(b->aux_stream); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
@@ -320,6 +332,7 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
     struct Tmp {
         PairHdr h;
         std::vector<PrimPair> pp;
+        std::vector<double2> ab;       // (exponent on A, exponent on B) of every primitive pair, same order as pp
     };
     std::vector<Tmp> tmp[MMDB_NCLASS_PAIR];
     for (int A = 0; A < nshell; ++A)
@@ -357,11 +370,21 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
                     // sqrt(pi)/2 of the asymptotic Boys function
                     q.cc = c2 * K * SQRT2_PI54 / (p * std::sqrt(p)) * std::sqrt(SQRTPI_2);
                     t.pp.push_back(q);
+                    t.ab.push_back(make_double2(ea, eb));
                 }
             if (t.pp.empty()) continue;
             // tight primitive pairs first: the slices of a virtual bra pair then hold primitives of similar exponent, and
             // the tight slices are far-field (asymptotic Boys branch) at almost any distance
-            std::stable_sort(t.pp.begin(), t.pp.end(), [](const PrimPair &x, const PrimPair &y) { return x.p > y.p; });
+            {
+                std::vector<int> ord(t.pp.size());
+                for (size_t x = 0; x < ord.size(); ++x) ord[x] = (int)x;
+                std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return t.pp[x].p > t.pp[y].p; });
+                std::vector<PrimPair> pp2(ord.size());
+                std::vector<double2> ab2(ord.size());
+                for (size_t x = 0; x < ord.size(); ++x) { pp2[x] = t.pp[ord[x]]; ab2[x] = t.ab[ord[x]]; }
+                t.pp.swap(pp2);
+                t.ab.swap(ab2);
+            }
             t.h.pnum = (int)t.pp.size();
             tmp[pc_index(sa.am, sb.am)].push_back(std::move(t));
         }
@@ -371,10 +394,12 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         // homogeneous contraction depth inside a warp: order by primitive-pair count (desc), stable
         std::stable_sort(v.begin(), v.end(), [](const Tmp &x, const Tmp &y) { return x.h.pnum > y.h.pnum; });
         P.npairs = (int)v.size();
+        std::vector<double2> prim_ab;
         for (auto &t : v) {
             t.h.poff = (int)P.prim.size();
             t.h.pad0 = (int)P.hdr.size();        // own index in the class (virtual pairs carry their parent's here)
             P.prim.insert(P.prim.end(), t.pp.begin(), t.pp.end());
+            prim_ab.insert(prim_ab.end(), t.ab.begin(), t.ab.end());
             P.hdr.push_back(t.h);
         }
         P.nprimpairs = (int64_t)P.prim.size();
@@ -393,6 +418,8 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         CU(cudaMalloc(&P.sh_dev, sizeof(int2) * P.npairs));
         CU(cudaMemcpy(P.hdr_dev, P.hdr.data(), sizeof(PairHdr) * P.npairs, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(P.prim_dev, P.prim.data(), sizeof(PrimPair) * P.prim.size(), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&P.prim_ab_dev, sizeof(double2) * prim_ab.size()));
+        CU(cudaMemcpy(P.prim_ab_dev, prim_ab.data(), sizeof(double2) * prim_ab.size(), cudaMemcpyHostToDevice));
         {   // structure-of-arrays copy for the bra side (see BraSrc in core.cuh); pairs are sorted by pnum (desc),
             // so primitive k exists for the first n_k pairs and row k holds exactly those
             const int kmax = P.hdr[0].pnum;
@@ -502,6 +529,8 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
 {
     const int L = la + lb + lc + ld;
     a.boys_tab = b->boys_dev[L];
+    CHK(ensure_eri_scratch(b));
+    a.scratch = b->eri_scratch_dev + ((b->aux_stream != nullptr && st == b->aux_stream) ? eri_scratch_region(b) : 0);
     const int key = ((la * 3 + lb) * 3 + lc) * 3 + ld;
     cudaError_t e = cudaSuccess;
     const int gridA = b->nsm;   // x occupancy inside launch_class
@@ -634,181 +663,186 @@ struct ScreenArgs {
     double tol;
     uint2 *list_far, *list_near;
     unsigned long long *ctr;       // see CTR_* below
+    unsigned *next_row;            // work counter: rows are handed to warps in order
 };
-enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_PER_LAUNCH = 6 };
+enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_ROW = 6, CTR_PER_LAUNCH = 7 };
+// list counters (CTR_NEAR / CTR_FAR / CTR_SLOW) count list SLOTS: multiples of 32, the padding of a warp's last block included
 
-constexpr int SCR_THREADS = 256;
-constexpr int SCR_CPT = 4;
-constexpr int SCR_TILE = SCR_THREADS * SCR_CPT;
+// Warp-autonomous screening (no block barriers, no serial sections):
+//   * a warp takes the next ket row from a global work counter and walks the row's columns in chunks of 256 (dead chunks
+//     are skipped on the chunk maxima: the columns are sorted by Schwarz half-decade inside a primitive-count group, so
+//     a weak ket pair touches only the leading chunks of every group);
+//   * phase 1 (density-independent bound, coalesced) appends survivors (column, row) to a per-warp PENDING buffer in
+//     shared memory; whenever 32 are pending, phase 2 (six-block density test, list classification, far-field test)
+//     runs on them with all 32 lanes busy — pending entries carry their row, so they are carried across rows;
+//   * the three list buffers (far / near / slow) of the warp are flushed in blocks of EXACTLY 32 entries, one atomic per
+//     block, so list offsets stay multiples of 32 and every ERI warp reads one flush block: 32 entries that share the
+//     ket pair except where a block straddles a row boundary.  The final partial blocks of a warp are padded with
+//     null entries (SCR_NULL) which the ERI kernels skip.
+constexpr int SCR_THREADS = 128;
+constexpr int SCR_WARPS = SCR_THREADS / 32;
+constexpr unsigned SCR_NULL = LIST_NULL;
+constexpr unsigned SCR_RES = 8;          // flush blocks per list-space reservation
 
 __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
 {
-    __shared__ unsigned long long s_wcnt[SCR_THREADS / 32];
-    __shared__ unsigned long long s_wk[SCR_THREADS / 32];
-    __shared__ unsigned s_wcand[SCR_THREADS / 32];
-    __shared__ unsigned long long s_base[3];
-    __shared__ unsigned short s_slot[SCR_THREADS / 32][SCR_CPT * 32];    // compacted phase-1 survivors per warp
-    const int ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
-    const long long nblk = (long long)(s.row1 - s.row0) * ntile;
+    __shared__ uint2 s_pend[SCR_WARPS][64];
+    __shared__ uint2 s_buf[SCR_WARPS][3][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 *pend = s_pend[warp];
+    unsigned npend = 0, nbuf[3] = {0u, 0u, 0u};
+    unsigned long long kk = 0;            // primitive quartets (per lane)
+    unsigned ncand = 0, nq = 0;           // candidates, shell quartets (per lane)
     double dg4 = 0.0;
     if (!s.all_pass) dg4 = 4.0 * __longlong_as_double((long long)*s.dglob);
-    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int j = s.row0 + (int)(blk / ntile);
-        const int c0 = (int)(blk % ntile) * SCR_TILE;
-        if (s.nshards > 1 && (j % s.nshards) != s.shard) continue;
-        // columns are shell pairs in pair order (dense fill): the triangle i >= j is a column range
-        const int cstart = (s.same_class && s.parent_bra == nullptr) ? j : 0;
-        if (c0 + SCR_TILE <= cstart) continue;
-        const double qj = s.Qs_ket[j];
-        if (!s.all_pass && s.early) {
-            // dead tile (block-uniform test on the chunk maxima): nothing can pass, so skip the scans, barriers
-            // and atomics altogether.  The columns are sorted by Schwarz half-decade inside a primitive-count group,
-            // so for a weak ket pair all but the leading chunks of every group die here after one load.
-            bool tile_live = false;
-            for (int ch = c0 >> 8; ch <= ((c0 + SCR_TILE - 1) >> 8); ++ch)
-                if (ch * 256 < s.nbra && !(s.Qmax_bra[ch] * qj * dg4 < s.tol)) tile_live = true;
-            if (!tile_live) {
-                if (threadIdx.x == 0) {
-                    const int lo = max(c0, cstart), hi = min(c0 + SCR_TILE, s.nbra);
-                    if (hi > lo) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)(hi - lo));
-                }
-                continue;
-            }
+    const unsigned lt = (1u << lane) - 1u;
+
+    // one block of 32 entries of list `which` (0 far, 1 near, 2 slow) leaves the warp's buffer.  List space is reserved
+    // SCR_RES blocks at a time (one atomic per 32 * SCR_RES entries: every warp of the grid adds to the same three
+    // counters, and same-address atomics are served one after the other by the L2).
+    unsigned long long res_base[3] = {0ull, 0ull, 0ull};
+    unsigned res_left[3] = {0u, 0u, 0u};
+    auto put_block = [&](int which, uint2 e) {
+        if (res_left[which] == 0u) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(s.ctr + (which == 0 ? CTR_FAR : (which == 1 ? CTR_NEAR : CTR_SLOW)), 32ull * SCR_RES);
+            res_base[which] = __shfl_sync(0xffffffffu, base, 0);
+            res_left[which] = SCR_RES;
         }
-        const int2 cd = s.sh_ket[j];
-        const unsigned long long kj = (unsigned long long)s.K_ket[j];
-        // Two phases per warp (128 consecutive columns).  Phase 1: the cheap density-independent bound on
-        // all columns, lane-strided (coalesced), survivors compacted into a per-warp slot array in column
-        // order.  Phase 2: the six-block density test and list classification run on the compacted
-        // survivors only, lane n taking survivors [n R, n R + R).
-        const int wbase = c0 + warp * (SCR_CPT * 32);
-        unsigned bits = 0, fbits = 0, sbits = 0, ncand = 0, nq = 0;
-        int col[SCR_CPT];
-        unsigned long long kk = 0;
-        const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
-        double4 gk = make_double4(0.0, 0.0, 0.0, 0.0);
-        double qmin = 0.0;
-        if (s.split && s.geo_ket) { gk = s.geo_ket[j]; qmin = s.pmin_ket[j]; }
-        // warp-level early exit: this warp's columns cannot pass if even their largest bound fails
-        // (chunk maxima cover 256 consecutive pairs; a warp covers SCR_CPT * 32 of them)
-        bool warp_live = s.all_pass || !s.early;
-        {
-            const int first = wbase, last = first + SCR_CPT * 32 - 1;
-            for (int wchunk = first >> 8; wchunk <= (last >> 8); ++wchunk)
-                if (wchunk * 256 < s.nbra && !(s.Qmax_bra[wchunk] * qj * dg4 < s.tol)) warp_live = true;
-        }
-        unsigned total = 0;
-#pragma unroll
-        for (int k = 0; k < SCR_CPT; ++k) {
-            const int off = k * 32 + lane;
-            const int i = wbase + off;
-            bool cand = (i < s.nbra) && (i >= cstart);
-            if (cand && s.same_class && s.parent_bra != nullptr && warp_live) cand = s.parent_bra[i] >= j;
-            ncand += cand ? 1u : 0u;            // candidates are counted for the statistics even when the warp exits early
-            bool p1 = cand && warp_live;
-            if (p1 && !s.all_pass) p1 = !(s.Qs_bra[i] * qj * dg4 < s.tol);
-            const unsigned m = __ballot_sync(0xffffffffu, p1);
-            if (p1) s_slot[warp][total + __popc(m & ((1u << lane) - 1u))] = (unsigned short)off;
-            total += __popc(m);
+        const unsigned long long pos = res_base[which] + lane;
+        if (which == 0) s.list_far[pos] = e;
+        else if (which == 1) s.list_near[pos] = e;
+        else s.list_near[s.cap - 1 - (long long)pos] = e;
+        res_base[which] += 32ull;
+        res_left[which] -= 1u;
+    };
+    auto flush = [&](int which, bool pad) {
+        uint2 e = s_buf[warp][which][lane];
+        if (pad && lane >= nbuf[which]) e = make_uint2(SCR_NULL, 0u);
+        put_block(which, e);
+        __syncwarp();
+        if (!pad) {
+            if (lane + 32u < nbuf[which]) e = s_buf[warp][which][lane + 32];
+            __syncwarp();
+            if (lane + 32u < nbuf[which]) s_buf[warp][which][lane] = e;
+            nbuf[which] -= 32u;
+        } else {
+            nbuf[which] = 0u;
         }
         __syncwarp();
-        const unsigned per = (total + 31u) >> 5;      // survivors per lane (<= SCR_CPT)
-#pragma unroll
-        for (int k = 0; k < SCR_CPT; ++k) {
-            col[k] = 0;
-            const unsigned n = lane * per + k;
-            if ((unsigned)k < per && n < total) {
-                const int i = wbase + s_slot[warp][n];
-                col[k] = i;
-                bool pass = true;
-                int2 ab = make_int2(0, 0);
-                if (!s.all_pass) {
-                    const double qq = s.Qs_bra[i] * qj;
-                    ab = s.sh_bra[i];
-                    const double *DS = s.DS;
-                    const int ns = s.nshell;
-                    double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
-                    dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
-                                           fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
-                    pass = !(qq * dmax < s.tol);
-                }
-                if (pass) {
-                    bits |= 1u << k;
-                    kk += (unsigned long long)s.K_bra[i] * kj;
-                    nq += (s.slice_bra == nullptr || s.slice_bra[i] == 0) ? 1u : 0u;
-                    if (s.split) {
-                        // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
-                        const bool slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
-                        if (slow) {
-                            sbits |= 1u << k;
-                        } else if (s.geo_bra) {
-                            // far field: every product centre of the bra slice lies in the sphere gb, every one of the ket
-                            // pair in gk, so |PQ| >= d for every primitive quartet; alpha >= pmin qmin / (pmin + qmin)
-                            const double4 gb = s.geo_bra[i];
-                            const double dx = gb.x - gk.x, dy = gb.y - gk.y, dz = gb.z - gk.z;
-                            const double d = sqrt(dx * dx + dy * dy + dz * dz) - gb.w - gk.w;
-                            const double pm = s.pmin_bra[i];
-                            if (d > 0.0 && (pm * qmin) * (d * d) >= s.tmax * (pm + qmin)) fbits |= 1u << k;
-                        }
+    };
+    // phase 2 on the first min(32, npend) pending candidates
+    auto process = [&]() {
+        const bool have = lane < npend;
+        int which = -1;
+        uint2 ent = make_uint2(0u, 0u);
+        if (have) {
+            ent = pend[lane];
+            const int i = (int)ent.x, j = (int)ent.y;
+            bool pass = true;
+            int2 ab = make_int2(0, 0);
+            const int2 cd = s.sh_ket[j];
+            if (!s.all_pass) {
+                const double qq = s.Qs_bra[i] * s.Qs_ket[j];
+                ab = s.sh_bra[i];
+                const double *DS = s.DS;
+                const int ns = s.nshell;
+                double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
+                dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
+                                       fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
+                pass = !(qq * dmax < s.tol);
+            }
+            if (pass) {
+                kk += (unsigned long long)s.K_bra[i] * (unsigned long long)s.K_ket[j];
+                nq += (s.slice_bra == nullptr || s.slice_bra[i] == 0) ? 1u : 0u;
+                which = 1;
+                if (s.split) {
+                    // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
+                    const bool slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == max(s.bf0[cd.x], s.bf0[cd.y]);
+                    if (slow) {
+                        which = 2;
+                    } else if (s.geo_bra) {
+                        // far field: every product centre of the bra slice lies in the sphere gb, every one of the ket
+                        // pair in gk, so |PQ| >= d for every primitive quartet; alpha >= pmin qmin / (pmin + qmin)
+                        const double4 gb = s.geo_bra[i], gk = s.geo_ket[j];
+                        const double dx = gb.x - gk.x, dy = gb.y - gk.y, dz = gb.z - gk.z;
+                        const double d = sqrt(dx * dx + dy * dy + dz * dz) - gb.w - gk.w;
+                        const double pm = s.pmin_bra[i], qm = s.pmin_ket[j];
+                        if (d > 0.0 && (pm * qm) * (d * d) >= s.tmax * (pm + qm)) which = 0;
                     }
                 }
             }
         }
-        // block-wide exclusive scan of the survivor counts: far | near << 21 | slow << 42
-        const unsigned nfar = __popc(fbits), nslow = __popc(sbits), nnear = __popc(bits) - nfar - nslow;
-        unsigned long long incl = (unsigned long long)nfar | ((unsigned long long)nnear << 21) | ((unsigned long long)nslow << 42);
-        const unsigned long long mine = incl;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+        for (int w = 0; w < 3; ++w) {
+            const unsigned m = __ballot_sync(0xffffffffu, which == w);
+            if (which == w) s_buf[warp][w][nbuf[w] + __popc(m & lt)] = ent;
+            nbuf[w] += __popc(m);
         }
-        unsigned long long ks = kk;
-        unsigned cs = ncand | (nq << 16);      // candidates | shell quartets (<= SCR_CPT each per thread)
+        __syncwarp();
+        // drop the processed candidates from the pending buffer
+        uint2 mv = make_uint2(0u, 0u);
+        if (lane + 32u < npend) mv = pend[lane + 32];
+        __syncwarp();
+        if (lane + 32u < npend) pend[lane] = mv;
+        npend = npend > 32u ? npend - 32u : 0u;
+        __syncwarp();
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ks += __shfl_xor_sync(0xffffffffu, ks, o);
-            cs += __shfl_xor_sync(0xffffffffu, cs, o);
-        }
-        if (lane == 31) s_wcnt[warp] = incl;
-        if (lane == 0) { s_wk[warp] = ks; s_wcand[warp] = cs; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long tot = 0, tk = 0;
-            unsigned tc = 0, tq = 0;
-            for (int w = 0; w < SCR_THREADS / 32; ++w) {
-                const unsigned long long c = s_wcnt[w];
-                s_wcnt[w] = tot;
-                tot += c;
-                tk += s_wk[w];
-                tc += s_wcand[w] & 0xffffu;
-                tq += s_wcand[w] >> 16;
+        for (int w = 0; w < 3; ++w)
+            if (nbuf[w] >= 32u) flush(w, false);
+    };
+
+    const int nchunk = (s.nbra + 255) >> 8;
+    for (;;) {
+        int j = 0;
+        if (lane == 0) j = s.row0 + (int)atomicAdd(s.next_row, 1u);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= s.row1) break;
+        if (s.nshards > 1 && (j % s.nshards) != s.shard) continue;
+        const double qj = s.Qs_ket[j];
+        // columns are shell pairs in pair order (dense fill): the triangle i >= j is a column range
+        const int cstart = (s.same_class && s.parent_bra == nullptr) ? j : 0;
+        for (int ch = cstart >> 8; ch < nchunk; ++ch) {
+            if (!s.all_pass && s.early && (s.Qmax_bra[ch] * qj * dg4 < s.tol)) {
+                ncand += (lane == 0) ? (unsigned)(min(s.nbra, (ch + 1) << 8) - max(cstart, ch << 8)) : 0u;   // statistics only
+                continue;
             }
-            if (tq) atomicAdd(s.ctr + CTR_NQUART, (unsigned long long)tq);
-            const unsigned tf = (unsigned)(tot & 0x1fffffull), tn = (unsigned)((tot >> 21) & 0x1fffffull), tsl = (unsigned)(tot >> 42);
-            s_base[0] = tf ? atomicAdd(s.ctr + CTR_FAR, (unsigned long long)tf) : 0ull;
-            s_base[1] = tn ? atomicAdd(s.ctr + CTR_NEAR, (unsigned long long)tn) : 0ull;
-            s_base[2] = tsl ? atomicAdd(s.ctr + CTR_SLOW, (unsigned long long)tsl) : 0ull;
-            if (tk) atomicAdd(s.ctr + CTR_PRIMQ, tk);
-            if (tc) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)tc);
+#pragma unroll 1
+            for (int sub = 0; sub < 8; ++sub) {
+                const int i = (ch << 8) + (sub << 5) + lane;
+                bool cand = (i < s.nbra) && (i >= cstart);
+                if (cand && s.same_class && s.parent_bra != nullptr) cand = s.parent_bra[i] >= j;
+                ncand += cand ? 1u : 0u;
+                bool p1 = cand;
+                if (p1 && !s.all_pass) p1 = !(s.Qs_bra[i] * qj * dg4 < s.tol);
+                const unsigned m = __ballot_sync(0xffffffffu, p1);
+                if (m == 0u) continue;
+                if (p1) pend[npend + __popc(m & lt)] = make_uint2((unsigned)i, (unsigned)j);
+                npend += __popc(m);
+                __syncwarp();
+                if (npend >= 32u) process();
+            }
         }
-        __syncthreads();
-        if (bits) {
-            const unsigned long long excl = s_wcnt[warp] + (incl - mine);
-            long long fpos = (long long)(s_base[0] + (excl & 0x1fffffull));
-            long long npos = (long long)(s_base[1] + ((excl >> 21) & 0x1fffffull));
-            long long spos = s.cap - 1 - (long long)(s_base[2] + (excl >> 42));
+    }
+    while (npend > 0u) process();
 #pragma unroll
-            for (int k = 0; k < SCR_CPT; ++k)
-                if (bits & (1u << k)) {
-                    const uint2 ent = make_uint2((unsigned)col[k], (unsigned)j);
-                    if (sbits & (1u << k)) s.list_near[spos--] = ent;
-                    else if (fbits & (1u << k)) s.list_far[fpos++] = ent;
-                    else s.list_near[npos++] = ent;
-                }
-        }
-        __syncthreads();
+    for (int w = 0; w < 3; ++w) {
+        if (nbuf[w] > 0u) flush(w, true);
+        while (res_left[w] > 0u) put_block(w, make_uint2(SCR_NULL, 0u));      // unused part of the last reservation
+    }
+    // statistics: one atomic per counter and warp
+    unsigned long long ks = kk;
+    unsigned cs = ncand, qs = nq;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ks += __shfl_xor_sync(0xffffffffu, ks, o);
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+        qs += __shfl_xor_sync(0xffffffffu, qs, o);
+    }
+    if (lane == 0) {
+        if (ks) atomicAdd(s.ctr + CTR_PRIMQ, ks);
+        if (cs) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)cs);
+        if (qs) atomicAdd(s.ctr + CTR_NQUART, (unsigned long long)qs);
     }
 }
 
@@ -830,6 +864,7 @@ __global__ void scatter_dense_kernel(const uint2 *list, const unsigned long long
         const int bb = f % nb;
         const int a = f / nb;
         const uint2 ij = list[e];
+        if (ij.x == LIST_NULL) continue;                               // padding entry
         const PairHdr bh = braH[ij.x], kh = ketH[ij.y];
         const size_t i = bh.bfA + a, j = bh.bfB + bb, k = kh.bfA + c, l = kh.bfB + d;
         // duplicates inside diagonal blocks ((a,b)/(b,a) of one shell, (ab|cd)/(cd|ab) of one pair) are
@@ -908,6 +943,16 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
     return MMDB_OK;
 }
 
+// resident warps of the screening kernel: every one may pad each list with up to 31 null entries
+static int screen_grid(const mmdb_basis *b) { return b->nsm * 12; }
+static size_t screen_pad(const mmdb_basis *b, size_t rows) { return std::min<size_t>(rows + SCR_WARPS, (size_t)screen_grid(b) * SCR_WARPS) * 32 * SCR_RES; }
+
+static bool far_enabled(int L)
+{
+    static const int far_maxl = getenv("MMDB_NO_FAR_LIST") ? -1 : (getenv("MMDB_FAR_MAXL") ? atoi(getenv("MMDB_FAR_MAXL")) : 3);
+    return L <= far_maxl;
+}
+
 // use_vp: columns are the bra class's virtual pairs (direct builds); otherwise its shell pairs (dense fill)
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
                       bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, uint2 *list_far,
@@ -930,10 +975,15 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
     s.ctr = b->ctr_dev + CTR_PER_LAUNCH * slot;
     s.early = getenv("MMDB_SCREEN_NO_EARLY_EXIT") ? 0 : 1;
     s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
-    if (getenv("MMDB_NO_FAR_LIST")) { s.geo_bra = nullptr; }       // A/B switch: everything block-digestible goes to the near list
-    const long long ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
-    const long long nblk = (long long)(row1 - row0) * ntile;
-    const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 32);
+    // The far-field list pays where Boys + R dominate a primitive quartet (L <= 3); above that the two extra launches per
+    // class pair cost more than the table branch they save.  MMDB_NO_FAR_LIST / MMDB_FAR_MAXL: A/B switches.
+    if (!far_enabled(B.la + B.lb + K.la + K.lb)) s.geo_bra = nullptr;
+    s.next_row = reinterpret_cast<unsigned *>(s.ctr + CTR_ROW);        // zeroed with the counters
+    // enough warps to fill the GPU on the big class pairs, but at least ~64k candidates per warp: every warp leaves one
+    // partly filled 32-entry block per list behind, and an ERI warp that gets such a block runs with idle lanes
+    const long long cand = (long long)(row1 - row0) * s.nbra / (nshards > 0 ? nshards : 1);
+    const long long want = std::max<long long>(1, cand / 65536 / SCR_WARPS);
+    const int grid = (int)std::min<long long>(std::min<long long>(want, ((long long)(row1 - row0) + SCR_WARPS - 1) / SCR_WARPS), (long long)screen_grid(b));
     if (grid > 0) screen_kernel<<<grid, SCR_THREADS, 0, st>>>(s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MMDB_ERR_CUDA, std::string("screen kernel: ") + cudaGetErrorString(e));
@@ -958,10 +1008,10 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
             const size_t nfn = (size_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
-            size_t rows_per = std::max<size_t>(1, std::min(LIST_CAP, SCRATCH_CAP / nfn) / (size_t)B.npairs);
+            size_t rows_per = std::max<size_t>(1, std::min(LIST_CAP, SCRATCH_CAP / nfn) / ((size_t)B.npairs + 32));
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                const size_t cap = (size_t)(row1 - row0) * B.npairs;
+                const size_t cap = (size_t)(row1 - row0) * B.npairs + screen_pad(b, (size_t)(row1 - row0));
                 CHK(ensure_list(b, cap));
                 CHK(ensure_scratch(b, cap * nfn));
                 if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
@@ -1020,7 +1070,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             const bool small = !timing && (size_t)B.npairs * K.npairs / nshards <= AUX_MAX_CANDIDATES;
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.nvp;   // room for every virtual pair
+                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.nvp + 2 * screen_pad(b, (size_t)(row1 - row0));   // room for every virtual pair + the padding of the flush blocks (near and slow share a buffer)
                 tasks.push_back(Task{cb, ck, row0, row1, cap, small});
                 (small ? cap_aux : cap_main) = std::max(small ? cap_aux : cap_main, cap);
             }
@@ -1107,7 +1157,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             // far-field list (asymptotic Boys branch only), near list, then the slow list (diagonal-type quartets /
             // complex density / deterministic mode)
             a.list = list_far; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_FAR;
-            CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST_FAR, 0, s1));
+            if (far_enabled(B.la + B.lb + K.la + K.lb)) CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST_FAR, 0, s1));
             a.list = list_near; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_NEAR;
             CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST, 0, s1));
             a.list = list_near + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_SLOW;

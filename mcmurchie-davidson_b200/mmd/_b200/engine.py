@@ -390,6 +390,32 @@ class Engine(object):
                 np.ascontiguousarray(M[:, u][:, :, u]), np.ascontiguousarray(Lm[:, u][:, :, u]))
 
 
+    # ---- nuclear gradient (cython/grad.pyx + mmd/forces.py) ----------------------------------------
+    def gradient(self, charges, coords, atom_of_function, P, F):
+        """dE/dX (natom, 3) of the RHF energy split into (one-electron, two-electron, nuclear repulsion) parts.
+        P = C_occ C_occ^T and F in user function order; atom_of_function[i] = atom index of basis function i."""
+        Z = np.ascontiguousarray(charges, dtype=np.float64)
+        xyz = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1)
+        natom = len(Z)
+        t = self.table
+        if self._schwarz is None:
+            self.schwarz()
+        P = np.real(np.asarray(P))
+        W = P @ np.real(np.asarray(F)) @ P                      # energy-weighted density (mmd/forces.py:94)
+        Pd = np.ascontiguousarray(t.to_dev_matrix(np.ascontiguousarray(P)), dtype=np.float64)
+        Wd = np.ascontiguousarray(t.to_dev_matrix(np.ascontiguousarray(W)), dtype=np.float64)
+        atom_of_function = np.asarray(atom_of_function)
+        shell_atom = np.zeros(t.nshell, dtype=np.int32)
+        for s in range(t.nshell):
+            users = t.dev2user[t.bf0[s]:t.bf0[s] + (int(t.am[s]) + 1) * (int(t.am[s]) + 2) // 2]
+            users = users[users >= 0]
+            shell_atom[s] = int(atom_of_function[users[0]])
+        g1 = np.zeros((natom, 3)); g2 = np.zeros((natom, 3)); gn = np.zeros((natom, 3))
+        L.check(self.lib.mmdb_gradient_host(self.h, natom, L.ptr(Z), L.ptr(xyz), L.ptr(shell_atom), L.ptr(Pd), L.ptr(Wd),
+                                            L.ptr(g1), L.ptr(g2), L.ptr(gn)))
+        return g1, g2, gn
+
+
 # ---- engines -------------------------------------------------------------------------------------------------
 # A Molecule OWNS its engine (mmd/molecule.py keeps it in self._engine, rebuilt by formBasis), so nothing another
 # molecule or an element-wise call does can evict it.  Everything else (the module-level ERI / S / T / V / formPT /

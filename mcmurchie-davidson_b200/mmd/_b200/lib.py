@@ -86,6 +86,7 @@ SIGNATURES = {
     "mmdb_schwarz_host": (C.c_int, [_vp, _vp]),
     "mmdb_eri_dense_host": (C.c_int, [_vp, _vp]),
     "mmdb_onee_host": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mmdb_gradient_host": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmdb_ao2mo_mp2": (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _dp, _vp]),
     "mmdb_boys_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp]),
     "mmdb_boys_class_host": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp]),

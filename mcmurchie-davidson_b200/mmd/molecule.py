@@ -144,11 +144,28 @@ class Molecule(SCF):
         self.TwoE = np.asarray(doERIs(N, self.TwoE, self.bfs))
 
     def forces(self):
-        """Nuclear gradient (mmd/forces.py of the reference).  Not part of the accelerated path yet: the device
-        side of the derivative integrals is not built, and this package has no CPU fallback
-        by design — fail loudly instead of returning slow or approximate forces."""
-        raise NotImplementedError("Molecule.forces(): derivative ERIs / gradient J/K are not built on the B200 path yet "
-                                  "(see DESIGN.md section 8); the CPU oracle (oracle.forces) is test infrastructure only")
+        """Nuclear forces of the converged RHF state (mmd/forces.py of the reference): atom.forces = -dE/dX for every
+        atom.  Derivative one- and two-electron integrals are evaluated on the device (csrc/grad.cu) and contracted
+        with the densities as they are produced — the reference's N^4 derivative tensor per atom and direction is
+        never formed, so forces also work after a direct SCF (no mol.TwoE needed)."""
+        if not getattr(self, "is_converged", False):
+            sys.exit("Need to converge SCF before computing gradient")
+        atom_of_function = np.zeros(self.nbasis, dtype=np.int64)
+        for k, atom in enumerate(self.atoms):
+            atom_of_function[atom._bf_range[0]:atom._bf_range[1]] = k
+        Z = [atom.charge for atom in self.atoms]
+        xyz = [atom.origin for atom in self.atoms]
+        g1, g2, gn = self.engine.gradient(Z, xyz, atom_of_function, self.P, self.F)
+        self.gradient_parts = {"one_electron": g1, "two_electron": g2, "nuclear": gn}
+        total = g1 + g2 + gn
+        for k, atom in enumerate(self.atoms):
+            atom.forces = -total[k]              # strictly dE/dX was computed; F = -dE/dX
+        return self._forces
+
+    @property
+    def _forces(self):
+        """(natom, 3) array of the forces last computed (mmd/molecule.py:48-53 of the reference)."""
+        return np.concatenate([atom.forces for atom in self.atoms]).reshape(-1, 3)
 
     def save_integrals(self, folder=None):
         """Crawford-format text dump (enuc, nbf, nelec, s, t, v, eri with 1-based indices)."""

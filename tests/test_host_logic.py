@@ -200,11 +200,13 @@ def test_device_resident_scf_loop_matches_host_loop(monkeypatch, direct):
     assert np.abs(np.asarray(dev.mu) - np.asarray(host.mu)).max() < 1e-7
 
 
-def test_forces_fail_loudly_until_the_gradient_path_exists():
-    from mmd._b200 import synth
+def test_forces_need_a_converged_scf():
+    """Molecule.forces() mirrors the reference's guard (mmd/forces.py:11-12): no gradient before the SCF has converged."""
     from mmd.molecule import Molecule
-    mol = Molecule(synth.water(), "sto-3g")
-    with pytest.raises(NotImplementedError):
+    from mmd._b200 import synth
+    mol = Molecule.__new__(Molecule)
+    mol.is_converged = False
+    with pytest.raises(SystemExit):
         mol.forces()
 
 

@@ -7,7 +7,7 @@ for spec in "$@"; do
   cls=${spec%%:*}; name=${spec##*:}
   pat=$(echo "$cls" | sed 's/\([0-9]\)/\\(int\\)\1/g')
   ncu --set full --import-source on --clock-control none --kernel-name-base demangled \
-      -k "regex:eri_(class|team)_kernel<${pat}, \(int\)1>" -c 1 -o gpurun_out/${pre}_${name} \
+      -k "regex:eri_(class|team)_kernel<${pat}, \(int\)1(, \(bool\)${FAR:-0})?>" -c 1 -o gpurun_out/${pre}_${name} \
       python tools/profile_direct.py ${WORKLOAD:-w32_ccpvdz} 1 > gpurun_out/${pre}_${name}.log 2>&1
   ls -la gpurun_out/${pre}_${name}.ncu-rep
 done
