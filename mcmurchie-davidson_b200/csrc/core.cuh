@@ -718,8 +718,11 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
             if constexpr (SCR_OUT) {
 #pragma unroll
                 for (int cdi = 0; cdi < NCDC; ++cdi) {
+                    // first bra primitive: plain store; later ones: fire-and-forget reductions (a read-modify-write would
+                    // chain NAB * NCDC dependent L2 round trips per bra primitive).  The reader uses ld.global.cg.
                     double *o = outg + (long long)(ab * NCDC + cdi) * ostride;
-                    *o = (ib == ib0) ? acc[cdi] : (*o + acc[cdi]);
+                    if (ib == ib0) __stcg(o, acc[cdi]);
+                    else red_add_f64(o, acc[cdi]);
                 }
             }
         });
@@ -816,8 +819,6 @@ enum { EPI_STORE = 0, EPI_DIGEST = 1, EPI_DIGEST_SLOW = 2 };
 // quartets) are thereby spread over up to 8 threads; J/K digestion is linear in the integrals, so every slice
 // digests its own partial block.  Bounds the longest serial thread (the tail of every launch).
 constexpr int BRA_SLICE = 8;
-// padding entry of the compact quartet lists (the screening kernel flushes blocks of exactly 32 entries): skipped by the consumers
-constexpr unsigned LIST_NULL = 0xffffffffu;
 constexpr unsigned SLICE_SHIFT = 24;
 constexpr unsigned PAIR_MASK = (1u << SLICE_SHIFT) - 1u;
 

@@ -35,21 +35,13 @@ struct PairClass {
     int la = 0, lb = 0;
     int npairs = 0;
     int64_t nprimpairs = 0;
-    // ---- virtual bra pairs (direct builds): one per slice of <= BRA_SLICE primitive pairs of a shell pair, primitives
-    // sorted by total exponent (tight first), virtual pairs sorted by (primitive count, Schwarz half-decade, Morton code
-    // of the pair centre).  Rebuilt whenever the Schwarz data change (build_virtual_pairs in lib.cu).
-    int nvp = 0;
-    mmdb::PairHdr *vhdr_dev = nullptr;   // [nvp] header of the slice: pnum = primitives of the slice, pad0 = parent pair, pad1 = slice index
-    double *vsoa_dev = nullptr;          // [8][nprimpairs] structure-of-arrays copy keyed by virtual pair (BraSrc)
-    long long *vrow_dev = nullptr;       // [BRA_SLICE]
-    double *vQs_dev = nullptr;           // [nvp] Schwarz bound of the parent pair
-    double *vQmax_dev = nullptr;         // [ceil(nvp/256)]
-    int *vK_dev = nullptr;               // [nvp] primitives in the slice
-    int *vparent_dev = nullptr;          // [nvp] index of the parent shell pair in this class
-    int *vslice_dev = nullptr;           // [nvp] slice index inside the parent pair (0 = counts as the shell quartet)
-    int2 *vsh_dev = nullptr;             // [nvp] (shA, shB)
-    double4 *vgeo_dev = nullptr;         // [nvp] bounding sphere of the slice's product centres (x, y, z, radius)
-    double *vpmin_dev = nullptr;         // [nvp] smallest total exponent in the slice
+    size_t slice_entries = 0;   // sum over pairs of ceil(pnum / BRA_SLICE): list entries one ket row can produce
+    // far-field test of the screening kernel: bounding sphere of the product centres (x, y, z, radius) and smallest total
+    // exponent — per SLICE of <= BRA_SLICE primitive pairs (bra side; primitives sorted by exponent, tight first) ...
+    int *sbase_dev = nullptr;            // [npairs] first slice record of a pair
+    double4 *sgeo_dev = nullptr;         // [slice_entries]
+    double *spmin_dev = nullptr;         // [slice_entries]
+    // ... and per whole pair (ket side)
     double4 *geo_dev = nullptr;          // [npairs] the same for the whole pair (ket side of the far-field test)
     double *pmin_dev = nullptr;          // [npairs]
     std::vector<mmdb::PairHdr> hdr;

@@ -184,7 +184,9 @@ __global__ void __launch_bounds__((JKB_QB + 1) * 32) jk_incore_bulk_kernel(const
     const int nqb = (N + JKB_QB - 1) / JKB_QB;
     const size_t N2 = (size_t)N * N;
     const int n2 = N >> 1;                                                                         // double2 columns
-    const size_t stage_elems = (size_t)JKB_QB * N;
+    // a stage = QB rows of T + the density row P[x][:] (+ its imaginary part): the consumers read everything from shared
+    // memory, the L1 (mostly carved out as shared memory here) is not on the streaming path at all
+    const size_t stage_elems = (size_t)JKB_QB * N + (size_t)(CPLX ? 2 : 1) * N;
     if (threadIdx.x == 0) {
         for (int s = 0; s < JKB_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], JKB_QB); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,8 +204,11 @@ __global__ void __launch_bounds__((JKB_QB + 1) * 32) jk_incore_bulk_kernel(const
                 for (int x = 0; x < N; ++x, ++it) {
                     const int s = (int)(it % JKB_STAGES);
                     if (it >= JKB_STAGES) mbar_wait(&empty[s], (unsigned)((it / JKB_STAGES - 1) & 1));
-                    mbar_expect_tx(&full[s], bytes);
+                    const unsigned pbytes = (unsigned)(N * sizeof(double));
+                    mbar_expect_tx(&full[s], bytes + (CPLX ? 2u : 1u) * pbytes);
                     bulk_g2s(buf + s * stage_elems, src0 + (size_t)x * N2, bytes, &full[s]);
+                    bulk_g2s(buf + s * stage_elems + (size_t)JKB_QB * N, Pre + (size_t)x * N, pbytes, &full[s]);
+                    if (CPLX) bulk_g2s(buf + s * stage_elems + (size_t)JKB_QB * N + N, Pim + (size_t)x * N, pbytes, &full[s]);
                 }
             }
         }
@@ -222,21 +227,22 @@ __global__ void __launch_bounds__((JKB_QB + 1) * 32) jk_incore_bulk_kernel(const
             const int s = (int)(it % JKB_STAGES);
             mbar_wait(&full[s], (unsigned)((it / JKB_STAGES) & 1));
             if (active) {
-                const double2 *row = reinterpret_cast<const double2 *>(buf + s * stage_elems + (size_t)warp * N);
-                const double2 *px = reinterpret_cast<const double2 *>(Pre + (size_t)x * N);
-                const double pxp = __ldg(Pre + (size_t)x * N + p);
-                const double pxpi = CPLX ? __ldg(Pim + (size_t)x * N + p) : 0.0;
+                const double *stg = buf + s * stage_elems;
+                const double2 *row = reinterpret_cast<const double2 *>(stg + (size_t)warp * N);
+                const double2 *px = reinterpret_cast<const double2 *>(stg + (size_t)JKB_QB * N);
+                const double pxp = stg[(size_t)JKB_QB * N + p];
+                const double pxpi = CPLX ? stg[(size_t)JKB_QB * N + N + p] : 0.0;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const int r = lane + 32 * v;
                     if (r < n2) {
                         const double2 m = row[r];
-                        const double2 a = __ldg(px + r);
+                        const double2 a = px[r];
                         kre = fma(m.x, a.x, fma(m.y, a.y, kre));
                         jr[v].x = fma(m.x, pxp, jr[v].x);
                         jr[v].y = fma(m.y, pxp, jr[v].y);
                         if (CPLX) {
-                            const double2 ai = __ldg(reinterpret_cast<const double2 *>(Pim + (size_t)x * N) + r);
+                            const double2 ai = reinterpret_cast<const double2 *>(stg + (size_t)JKB_QB * N + N)[r];
                             kim = fma(m.x, ai.x, fma(m.y, ai.y, kim));
                             ji[v].x = fma(m.x, pxpi, ji[v].x);
                             ji[v].y = fma(m.y, pxpi, ji[v].y);
@@ -296,7 +302,7 @@ extern "C" int mmdb_jk_incore(int device, const double *TwoE_dev, int N, const d
     const int nv = (cols + 31) / 32;      // column slots per lane, rounded up to a compiled size
     if (vec2 && !getenv("MMDB_JK_NO_BULK")) {
         // TMA bulk-copy pipeline: STAGES x (QB rows of N doubles) in flight per CTA
-        const size_t smem = 128 + (size_t)JKB_STAGES * JKB_QB * N * sizeof(double);
+        const size_t smem = 128 + (size_t)JKB_STAGES * ((size_t)JKB_QB * N + (cplx ? 2 : 1) * (size_t)N) * sizeof(double);
         const int tasks = N * ((N + JKB_QB - 1) / JKB_QB);
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / smem));
         const int gridb = std::min(tasks, nsm * per_sm);

@@ -24,7 +24,9 @@ __host__ __device__ constexpr int etab_size(int la, int lb)
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr bool scratch_out()
 {
-    return LA == 2 && LB == 1 && ncart(LC) * ncart(LD) >= 3;
+    // (dp|ps) (three ket component pairs in all) stays with one pair per thread and three CTAs per quartet: measured
+    // 6.5 ms against 6.9 ms with the scratch column; (dp|pp) went from 6.3 to 5.0 ms, (dp|ds) from 3.3 to 3.1 ms
+    return LA == 2 && LB == 1 && ncart(LC) * ncart(LD) >= 6;
 }
 
 // R_tuv lives in shared memory (one column per thread) for the high-L classes, in registers otherwise
@@ -304,6 +306,11 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
     }
     if (active) {
         const double tol = dg.tol;
+        // the block's integrals first: the reductions below are compiler barriers (asm volatile, memory clobber), a load
+        // issued between them would wait for its L2 round trip alone
+        double ov[NA * NB];
+#pragma unroll
+        for (int x = 0; x < NA * NB; ++x) ov[x] = (ostride == 1) ? out[x] : __ldcg(out + (long long)x * ostride);
         const double pcd = __ldg(&P[ocd]), qcd = __ldg(&SQ[ocd]);
         const double pcd4 = 4.0 * fabs(pcd);
         double Pbc[NB], Pbd[NB], Kbc[NB], Kbd[NB], Mb[NB];
@@ -331,7 +338,7 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
                 if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
                 const double dmax = fmax(4.0 * fabs(pab), fmax(ma, Mb[b]));
                 const double bound = (qab * qcd) * dmax;
-                const double e = (bound < tol) ? 0.0 : (s8 * wab * scd) * out[(long long)(a * NB + b) * ostride];
+                const double e = (bound < tol) ? 0.0 : (s8 * wab * scd) * ov[a * NB + b];
                 const double eq = -0.25 * e;
                 red_add_f64(&G[oab], pcd * e);
                 jcd = fma(pab, e, jcd);
@@ -406,7 +413,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
                         constexpr int cdi = decltype(CDI)::value;
                         constexpr int cd = CD0 + cdi;
                         constexpr double sc = sab * comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND);
-                        o[ab * NCD + cd] = scr[(long long)(ab * NCDC + cdi) * sstride] * sc;
+                        o[ab * NCD + cd] = __ldcg(scr + (long long)(ab * NCDC + cdi) * sstride) * sc;
                     });
                 });
             }
@@ -422,7 +429,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
             if (valid) {
                 double tmp[NAB * NCDC];
 #pragma unroll 1
-                for (int x = 0; x < NAB * NCDC; ++x) tmp[x] = scr[(long long)x * sstride];
+                for (int x = 0; x < NAB * NCDC; ++x) tmp[x] = __ldcg(scr + (long long)x * sstride);
                 if (a.dg.fixed) digest_block_slow<true>(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
                 else digest_block_slow<false>(a.dg, bh, kh, samePair, LA, LB, LC, LD, CD0, NCDC, tmp);
             }
@@ -515,16 +522,17 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD, FAR>(), min_blocks<
         for (; base < n; base += wstride) {
             if constexpr (LOCKSTEP) __syncthreads();
             const unsigned long long e = base + threadIdx.x;
+            const bool valid = e < n;
             uint2 ij = ij_next;
-            const bool valid = (e < n) && (ij.x != LIST_NULL);       // LIST_NULL: padding of a screening flush block
-            if (ij.x == LIST_NULL) ij.x = 0u;
-            // direct builds: ij.x indexes the class's VIRTUAL bra pairs (one slice of <= BRA_SLICE primitive pairs of a
-            // shell pair, lib.cu build_virtual_pairs), whose header carries the slice's own primitive range
+            // direct builds: the top byte of the bra index is the slice of <= BRA_SLICE primitive pairs this entry covers
+            const int slice = (EPI == EPI_STORE) ? 0 : (int)(ij.x >> SLICE_SHIFT);
+            if constexpr (EPI != EPI_STORE) ij.x &= PAIR_MASK;
             const PairHdr bh = ld_hdr(a.braH + ij.x);
             const PairHdr kh = ld_hdr(a.ketH + ij.y);
             if (base + wstride < n) ij_next = __ldg(a.list + (long long)min(e + wstride, n - 1) * lstep);
             const bool samePair = a.same_class && (bh.pad0 == (int)ij.y);       // pad0: (parent) pair index of the bra entry
-            const int ib0 = 0, ib1 = bh.pnum;
+            const int ib0 = (EPI == EPI_STORE) ? 0 : slice * BRA_SLICE;
+            const int ib1 = (EPI == EPI_STORE) ? bh.pnum : min(bh.pnum, ib0 + BRA_SLICE);
             bool ket_uniform = false;
             if constexpr (EPI == EPI_DIGEST) {
                 const unsigned y0 = __shfl_sync(0xffffffffu, ij.y, 0);
@@ -554,6 +562,8 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD, FAR>(), min_blocks<
 template <int LA, int LB, int LC, int LD>
 cudaError_t launch_class(const EriArgs &a, int kind, int grid, cudaStream_t st);
 
+constexpr int FAR_MAXL = 3;
+
 // launch kinds: the three epilogues + the far-field variant of the block digestion
 enum { LK_STORE = 0, LK_DIGEST = 1, LK_DIGEST_SLOW = 2, LK_DIGEST_FAR = 3, LK_COUNT = 4 };
 
@@ -576,11 +586,14 @@ template <int LA, int LB, int LC, int LD>
 cudaError_t launch_class_impl(const EriArgs &a, int kind, int grid, cudaStream_t st)
 {
     static int occ[LK_COUNT] = {0, 0, 0, 0};
+    // far-field variants exist for L <= FAR_MAXL only: above that Boys + R are a small part of a primitive quartet and the
+    // extra launch per class pair costs more than the table branch it saves (lib.cu sends everything to the near list)
+    constexpr bool HAS_FAR = (LA + LB + LC + LD <= FAR_MAXL);
     if (occ[0] == 0) {
         setup_kernel<LA, LB, LC, LD, EPI_STORE, false>(&occ[LK_STORE]);
         setup_kernel<LA, LB, LC, LD, EPI_DIGEST, false>(&occ[LK_DIGEST]);
         setup_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW, false>(&occ[LK_DIGEST_SLOW]);
-        setup_kernel<LA, LB, LC, LD, EPI_DIGEST, true>(&occ[LK_DIGEST_FAR]);
+        if constexpr (HAS_FAR) setup_kernel<LA, LB, LC, LD, EPI_DIGEST, true>(&occ[LK_DIGEST_FAR]);
     }
     constexpr int NCH = block_chunks<LA, LB, LC, LD>() ? ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() : 1;
     auto shape = [&](int o) { return std::max(NCH, (grid * o) / NCH * NCH); };   // multiple of the chunk count
@@ -592,9 +605,11 @@ cudaError_t launch_class_impl(const EriArgs &a, int kind, int grid, cudaStream_t
         eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST, false><<<shape(occ[kind]), threads, smem, st>>>(a);
     else if (kind == LK_DIGEST_SLOW)
         eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW, false><<<shape(occ[kind]), threads, smem, st>>>(a);
-    else
+    else if constexpr (HAS_FAR)
         eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST, true><<<shape(occ[kind]), ka_threads<LA, LB, LC, LD, true>(),
                                                              class_smem_bytes<LA, LB, LC, LD, true>(), st>>>(a);
+    else
+        return cudaErrorInvalidValue;          // no far-field variant for this class
     return cudaGetLastError();
 }
 

@@ -96,7 +96,6 @@ static __global__ void __launch_bounds__(KB_THREADS) eri_generic_kernel(const Er
         const int cx = cart_pow_rt(lc, c, 0), cy = cart_pow_rt(lc, c, 1), cz = cart_pow_rt(lc, c, 2);
         const int dx = cart_pow_rt(ld, d, 0), dy = cart_pow_rt(ld, d, 1), dz = cart_pow_rt(ld, d, 2);
         const uint2 ij = __ldg(a.list + (long long)e * a.list_step);
-        if (ij.x == LIST_NULL) continue;                              // padding entry
         const PairHdr bh = ld_hdr(a.braH + ij.x);
         const PairHdr kh = ld_hdr(a.ketH + ij.y);
         double out[36];

@@ -131,8 +131,7 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     cudaSetDevice(b->device);
     for (auto &p : b->pc) {
         cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.prim_ab_dev); cudaFree(p.prim_soa_dev); cudaFree(p.prim_row_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
-        cudaFree(p.vhdr_dev); cudaFree(p.vsoa_dev); cudaFree(p.vrow_dev); cudaFree(p.vQs_dev); cudaFree(p.vQmax_dev); cudaFree(p.vK_dev);
-        cudaFree(p.vparent_dev); cudaFree(p.vslice_dev); cudaFree(p.vsh_dev); cudaFree(p.vgeo_dev); cudaFree(p.vpmin_dev); cudaFree(p.geo_dev); cudaFree(p.pmin_dev);
+        cudaFree(p.sbase_dev); cudaFree(p.sgeo_dev); cudaFree(p.spmin_dev); cudaFree(p.geo_dev); cudaFree(p.pmin_dev);
     }
     for (auto &t : b->boys_dev) cudaFree(t);
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
@@ -170,111 +169,6 @@ static void prim_bounds(const PrimPair *pp, int n, double4 *geo, double *pmin)
 }
 
 __global__ void qs_chunk_max_kernel(const double *Qs, int npairs, double *Qmax);
-
-// Virtual bra pairs of every class (see PairClass in handle.h).  Called whenever the Schwarz data change: the sort key
-// uses the Schwarz bound of the parent pair.  Host work: O(pairs log pairs) once per geometry.
-static int build_virtual_pairs(mmdb_basis *b)
-{
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (const ShellH &h : b->sh) {
-        const double c[3] = {h.x, h.y, h.z};
-        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], c[d]); hi[d] = std::max(hi[d], c[d]); }
-    }
-    double ext = 1e-6;
-    for (int d = 0; d < 3; ++d) ext = std::max(ext, hi[d] - lo[d]);
-    auto spread = [](unsigned v) {      // 10 bits -> every third bit
-        unsigned long long x = v & 0x3ffu;
-        x = (x | (x << 16)) & 0x30000ffull;
-        x = (x | (x << 8)) & 0x300f00full;
-        x = (x | (x << 4)) & 0x30c30c3ull;
-        x = (x | (x << 2)) & 0x9249249ull;
-        return x;
-    };
-    struct VP { int parent, slice, p0, pn; double qs; unsigned long long key; double4 geo; double pmin; };
-    for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
-        PairClass &P = b->pc[c];
-        if (P.npairs == 0) continue;
-        std::vector<double> Qs(P.npairs);
-        CU(cudaMemcpy(Qs.data(), P.Qs_dev, sizeof(double) * P.npairs, cudaMemcpyDeviceToHost));
-        std::vector<VP> v;
-        for (int i = 0; i < P.npairs; ++i) {
-            const PairHdr &h = P.hdr[i];
-            for (int p0 = 0, sl = 0; p0 < h.pnum; p0 += BRA_SLICE, ++sl) {
-                VP x;
-                x.parent = i; x.slice = sl; x.p0 = p0; x.pn = std::min(BRA_SLICE, h.pnum - p0); x.qs = Qs[i];
-                prim_bounds(&P.prim[h.poff + p0], x.pn, &x.geo, &x.pmin);
-                // key: primitive count (desc) | Schwarz half-decade (desc) | Morton code of the slice centre
-                int hd = 0;
-                if (x.qs > 0.0 && std::isfinite(x.qs)) hd = std::max(0, std::min(255, (int)std::floor(2.0 * std::log10(x.qs)) + 200));
-                const unsigned qx = (unsigned)(1023.0 * (x.geo.x - lo[0]) / ext), qy = (unsigned)(1023.0 * (x.geo.y - lo[1]) / ext),
-                               qz = (unsigned)(1023.0 * (x.geo.z - lo[2]) / ext);
-                const unsigned long long morton = spread(qx) | (spread(qy) << 1) | (spread(qz) << 2);
-                x.key = ((unsigned long long)(BRA_SLICE - x.pn) << 40) | ((unsigned long long)(255 - hd) << 32) | morton;
-                v.push_back(x);
-            }
-        }
-        std::stable_sort(v.begin(), v.end(), [](const VP &x, const VP &y) { return x.key < y.key; });
-        const int nvp = (int)v.size();
-        const long long nprim = (long long)P.prim.size();
-        std::vector<PairHdr> vh(nvp);
-        std::vector<double> vqs(nvp), vpm(nvp);
-        std::vector<int> vk(nvp), vpar(nvp), vsl(nvp);
-        std::vector<int2> vshl(nvp);
-        std::vector<double4> vg(nvp);
-        std::vector<long long> row(BRA_SLICE + 1, 0);
-        for (int k = 0; k < BRA_SLICE; ++k) {
-            long long nk = 0;
-            while (nk < nvp && v[nk].pn > k) ++nk;
-            row[k + 1] = row[k] + nk;
-        }
-        std::vector<double> soa((size_t)8 * nprim);
-        for (int i = 0; i < nvp; ++i) {
-            const VP &x = v[i];
-            PairHdr h = P.hdr[x.parent];
-            h.poff += x.p0; h.pnum = x.pn; h.pad0 = x.parent; h.pad1 = x.slice; h.Qs = x.qs;
-            vh[i] = h; vqs[i] = x.qs; vpm[i] = x.pmin; vk[i] = x.pn; vpar[i] = x.parent; vsl[i] = x.slice;
-            vshl[i] = make_int2(h.shA, h.shB); vg[i] = x.geo;
-            for (int k = 0; k < x.pn; ++k) {
-                const PrimPair &q = P.prim[h.poff + k];
-                const double f[8] = {q.Px, q.Py, q.Pz, q.p, q.cc, q.PAx, q.PAy, q.PAz};
-                for (int z = 0; z < 8; ++z) soa[(size_t)z * nprim + row[k] + i] = f[z];
-            }
-        }
-        if (P.nvp != nvp) {
-            cudaFree(P.vhdr_dev); cudaFree(P.vsoa_dev); cudaFree(P.vrow_dev); cudaFree(P.vQs_dev); cudaFree(P.vQmax_dev); cudaFree(P.vK_dev);
-            cudaFree(P.vparent_dev); cudaFree(P.vslice_dev); cudaFree(P.vsh_dev); cudaFree(P.vgeo_dev); cudaFree(P.vpmin_dev);
-            P.vhdr_dev = nullptr; P.vsoa_dev = nullptr; P.vrow_dev = nullptr; P.vQs_dev = nullptr; P.vQmax_dev = nullptr; P.vK_dev = nullptr;
-            P.vparent_dev = nullptr; P.vslice_dev = nullptr; P.vsh_dev = nullptr; P.vgeo_dev = nullptr; P.vpmin_dev = nullptr;
-            P.nvp = 0;
-            CU(cudaMalloc(&P.vhdr_dev, sizeof(PairHdr) * nvp));
-            CU(cudaMalloc(&P.vsoa_dev, sizeof(double) * soa.size()));
-            CU(cudaMalloc(&P.vrow_dev, sizeof(long long) * BRA_SLICE));
-            CU(cudaMalloc(&P.vQs_dev, sizeof(double) * nvp));
-            CU(cudaMalloc(&P.vQmax_dev, sizeof(double) * ((nvp + 255) / 256)));
-            CU(cudaMalloc(&P.vK_dev, sizeof(int) * nvp));
-            CU(cudaMalloc(&P.vparent_dev, sizeof(int) * nvp));
-            CU(cudaMalloc(&P.vslice_dev, sizeof(int) * nvp));
-            CU(cudaMalloc(&P.vsh_dev, sizeof(int2) * nvp));
-            CU(cudaMalloc(&P.vgeo_dev, sizeof(double4) * nvp));
-            CU(cudaMalloc(&P.vpmin_dev, sizeof(double) * nvp));
-            P.nvp = nvp;
-        }
-        CU(cudaMemcpy(P.vhdr_dev, vh.data(), sizeof(PairHdr) * nvp, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vsoa_dev, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vrow_dev, row.data(), sizeof(long long) * BRA_SLICE, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vQs_dev, vqs.data(), sizeof(double) * nvp, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vK_dev, vk.data(), sizeof(int) * nvp, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vparent_dev, vpar.data(), sizeof(int) * nvp, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vslice_dev, vsl.data(), sizeof(int) * nvp, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vsh_dev, vshl.data(), sizeof(int2) * nvp, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vgeo_dev, vg.data(), sizeof(double4) * nvp, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(P.vpmin_dev, vpm.data(), sizeof(double) * nvp, cudaMemcpyHostToDevice));
-        qs_chunk_max_kernel<<<((nvp + 255) / 256 + 3) / 4, 128>>>(P.vQs_dev, nvp, P.vQmax_dev);
-    }
-    CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
-    return MMDB_OK;
-}
 
 extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const int *nprim, const int *prim_off,
                                  const double *centre, const double *exps, const double *coefs, const int *bf0,
@@ -391,8 +285,23 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
     for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
         PairClass &P = b->pc[c];
         auto &v = tmp[c];
-        // homogeneous contraction depth inside a warp: order by primitive-pair count (desc), stable
-        std::stable_sort(v.begin(), v.end(), [](const Tmp &x, const Tmp &y) { return x.h.pnum > y.h.pnum; });
+        // homogeneous contraction depth inside a warp: order by primitive-pair count (desc); inside one depth by an ESTIMATE
+        // of the Schwarz bound (desc), so the pairs that can survive a weak ket row are a prefix of every depth group and
+        // the screening kernel drops the rest tile by tile on its chunk maxima (which use the exact bounds).  The estimate:
+        // sqrt of the s-type self-repulsion of the pair with F_0 <= 1,  sum_kl |cc_k cc_l| sqrt(p_k p_l / (p_k + p_l)).
+        const bool sort_q = getenv("MMDB_PAIR_SORT") ? atoi(getenv("MMDB_PAIR_SORT")) != 0 : true;
+        for (auto &t : v) {
+            double q = 0.0;
+            for (const PrimPair &x : t.pp)
+                for (const PrimPair &y : t.pp) q += std::fabs(x.cc * y.cc) * std::sqrt(x.p * y.p / (x.p + y.p));
+            t.h.Qs = sort_q ? std::sqrt(q) : 0.0;      // overwritten with the exact bound by mmdb_schwarz
+        }
+        std::stable_sort(v.begin(), v.end(), [](const Tmp &x, const Tmp &y) {
+            if (x.h.pnum != y.h.pnum) return x.h.pnum > y.h.pnum;
+            // half-decades: keeps the construction (A-major) order inside a bucket, i.e. neighbouring columns share a shell
+            const int bx = x.h.Qs > 0 ? (int)std::floor(2.0 * std::log10(x.h.Qs)) : -1000, by = y.h.Qs > 0 ? (int)std::floor(2.0 * std::log10(y.h.Qs)) : -1000;
+            return bx > by;
+        });
         P.npairs = (int)v.size();
         std::vector<double2> prim_ab;
         for (auto &t : v) {
@@ -404,6 +313,7 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         }
         P.nprimpairs = (int64_t)P.prim.size();
         if (P.npairs == 0) continue;
+        if ((unsigned)P.npairs > PAIR_MASK) return fail(MMDB_ERR_UNSUPPORTED, "more than 2^24 shell pairs in one class");
         std::vector<int> K(P.npairs);
         std::vector<int2> shs(P.npairs);
         for (int i = 0; i < P.npairs; ++i) {
@@ -451,6 +361,26 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
             CU(cudaMalloc(&P.pmin_dev, sizeof(double) * P.npairs));
             CU(cudaMemcpy(P.geo_dev, geo.data(), sizeof(double4) * P.npairs, cudaMemcpyHostToDevice));
             CU(cudaMemcpy(P.pmin_dev, pmin.data(), sizeof(double) * P.npairs, cudaMemcpyHostToDevice));
+            // the same per SLICE of <= BRA_SLICE primitive pairs (bra side: one list entry per slice)
+            std::vector<int> sbase(P.npairs);
+            std::vector<double4> sgeo;
+            std::vector<double> spmin;
+            for (int i = 0; i < P.npairs; ++i) {
+                sbase[i] = (int)sgeo.size();
+                for (int p0 = 0; p0 < P.hdr[i].pnum; p0 += BRA_SLICE) {
+                    double4 gq; double pm;
+                    prim_bounds(&P.prim[P.hdr[i].poff + p0], std::min(BRA_SLICE, P.hdr[i].pnum - p0), &gq, &pm);
+                    sgeo.push_back(gq);
+                    spmin.push_back(pm);
+                }
+            }
+            P.slice_entries = sgeo.size();
+            CU(cudaMalloc(&P.sbase_dev, sizeof(int) * P.npairs));
+            CU(cudaMalloc(&P.sgeo_dev, sizeof(double4) * sgeo.size()));
+            CU(cudaMalloc(&P.spmin_dev, sizeof(double) * spmin.size()));
+            CU(cudaMemcpy(P.sbase_dev, sbase.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(P.sgeo_dev, sgeo.data(), sizeof(double4) * sgeo.size(), cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(P.spmin_dev, spmin.data(), sizeof(double) * spmin.size(), cudaMemcpyHostToDevice));
         }
         CU(cudaMemset(P.Qs_dev, 0, sizeof(double) * P.npairs));
         CU(cudaMemcpy(P.K_dev, K.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
@@ -631,30 +561,28 @@ __global__ void qs_chunk_max_kernel(const double *Qs, int npairs, double *Qmax)
 }
 
 // Shell-level screen -> compact quartet lists.
-// Rows are KET pairs j in [row0,row1) (j % nshards == shard), columns are BRA pairs i: for direct builds the class's
-// VIRTUAL bra pairs (slices of <= BRA_SLICE primitive pairs, sorted by primitive count / Schwarz half-decade / Morton
-// code), for the dense fill the shell pairs themselves.  When the two classes coincide only columns whose (parent) pair
-// index is >= j are candidates.  One block handles one row x 1024 consecutive columns (two-phase, see the kernel),
-// block-wide prefix sum, ONE atomic per list and tile to reserve space.  Entries of a row are written in column order,
-// so consecutive list entries share the ket pair (warp-uniform in the ERI kernels: the inner primitive loop and the
-// J_cd reduction run on broadcast data) and walk bra pairs of one contraction depth that are close in space.
-// Direct builds get THREE lists per class pair:
+// Rows are KET pairs j in [row0,row1) (j % nshards == shard), columns are BRA pairs i (i >= j when the two classes
+// coincide).  One block handles one row x 1024 consecutive columns (two-phase, see the kernel), block-wide prefix sum,
+// ONE atomic per list and tile to reserve list space.  Entries of a row are written in column order, so consecutive
+// list entries share the ket pair (warp-uniform in the ERI kernels: the inner primitive loop and the J_cd reduction run
+// on broadcast data) and walk the bra pairs.  A direct build gets one entry per SLICE of <= BRA_SLICE bra primitive
+// pairs (slice id in the top byte of the bra index; the primitives of a pair are sorted by exponent, tight first) and
+// THREE lists per class pair:
 //   far   block-digestible entries all of whose primitive quartets are on the asymptotic Boys branch
-//         (alpha_min d_min^2 >= T_max(L) from the bounding spheres of the two sets of product centres),
+//         (alpha_min d_min^2 >= T_max(L) from the bounding spheres of the slice's and the ket pair's product centres),
 //   near  the other block-digestible entries,
 //   slow  diagonal-type quartets / complex densities / deterministic mode (per-function digestion).
 struct ScreenArgs {
     const double *Qs_bra, *Qs_ket, *Qmax_bra;
     const int2 *sh_bra, *sh_ket;
     const int *K_bra, *K_ket;
-    const int *parent_bra;         // parent shell pair of a virtual bra pair (nullptr: columns are shell pairs)
-    const int *slice_bra;          // slice index of a virtual bra pair (0 = counts as the shell quartet) or nullptr
-    const double4 *geo_bra, *geo_ket;      // bounding spheres of the product centres (far-field test) or nullptr
-    const double *pmin_bra, *pmin_ket;     // smallest total exponents
-    double tmax;                   // T_max(L) of the class pair (+ margin)
+    const int *sbase_bra;                  // first slice record of a bra pair
+    const double4 *sgeo_bra, *geo_ket;     // bounding spheres of the product centres: per bra slice / per ket pair (or nullptr)
+    const double *spmin_bra, *pmin_ket;    // smallest total exponent: per bra slice / per ket pair
+    double tmax;                           // T_max(L) of the class pair (+ margin)
     int nbra, row0, row1, same_class, shard, nshards, nshell, all_pass;
     int early;                     // warp-level early exit on the chunk maxima of the bra bounds
-    int split;                     // direct build: classify survivors into the far / near / slow lists
+    int split;                     // direct build: one entry per slice, classified into the far / near / slow lists
     int force_slow;                // complex density / deterministic mode: everything goes to the slow list
     const int *bf0;                // first function index per shell
     long long cap;                 // capacity of list_near (the slow list starts at list_near[cap-1] and grows downwards)
@@ -663,186 +591,191 @@ struct ScreenArgs {
     double tol;
     uint2 *list_far, *list_near;
     unsigned long long *ctr;       // see CTR_* below
-    unsigned *next_row;            // work counter: rows are handed to warps in order
 };
-enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_ROW = 6, CTR_PER_LAUNCH = 7 };
-// list counters (CTR_NEAR / CTR_FAR / CTR_SLOW) count list SLOTS: multiples of 32, the padding of a warp's last block included
+enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_PER_LAUNCH = 6 };
 
-// Warp-autonomous screening (no block barriers, no serial sections):
-//   * a warp takes the next ket row from a global work counter and walks the row's columns in chunks of 256 (dead chunks
-//     are skipped on the chunk maxima: the columns are sorted by Schwarz half-decade inside a primitive-count group, so
-//     a weak ket pair touches only the leading chunks of every group);
-//   * phase 1 (density-independent bound, coalesced) appends survivors (column, row) to a per-warp PENDING buffer in
-//     shared memory; whenever 32 are pending, phase 2 (six-block density test, list classification, far-field test)
-//     runs on them with all 32 lanes busy — pending entries carry their row, so they are carried across rows;
-//   * the three list buffers (far / near / slow) of the warp are flushed in blocks of EXACTLY 32 entries, one atomic per
-//     block, so list offsets stay multiples of 32 and every ERI warp reads one flush block: 32 entries that share the
-//     ket pair except where a block straddles a row boundary.  The final partial blocks of a warp are padded with
-//     null entries (SCR_NULL) which the ERI kernels skip.
-constexpr int SCR_THREADS = 128;
-constexpr int SCR_WARPS = SCR_THREADS / 32;
-constexpr unsigned SCR_NULL = LIST_NULL;
-constexpr unsigned SCR_RES = 8;          // flush blocks per list-space reservation
+constexpr int SCR_THREADS = 256;
+constexpr int SCR_CPT = 4;
+constexpr int SCR_TILE = SCR_THREADS * SCR_CPT;
+constexpr int SCR_MAXSL = 8;       // slices per pair the classification masks can hold (pairs with more go near/slow whole)
 
 __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
 {
-    __shared__ uint2 s_pend[SCR_WARPS][64];
-    __shared__ uint2 s_buf[SCR_WARPS][3][64];
+    __shared__ unsigned long long s_wcnt[SCR_THREADS / 32];
+    __shared__ unsigned long long s_wk[SCR_THREADS / 32];
+    __shared__ unsigned s_wcand[SCR_THREADS / 32];
+    __shared__ unsigned long long s_base[3];
+    __shared__ unsigned short s_slot[SCR_THREADS / 32][SCR_CPT * 32];    // compacted phase-1 survivors per warp
+    const int ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
+    const long long nblk = (long long)(s.row1 - s.row0) * ntile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint2 *pend = s_pend[warp];
-    unsigned npend = 0, nbuf[3] = {0u, 0u, 0u};
-    unsigned long long kk = 0;            // primitive quartets (per lane)
-    unsigned ncand = 0, nq = 0;           // candidates, shell quartets (per lane)
     double dg4 = 0.0;
     if (!s.all_pass) dg4 = 4.0 * __longlong_as_double((long long)*s.dglob);
-    const unsigned lt = (1u << lane) - 1u;
-
-    // one block of 32 entries of list `which` (0 far, 1 near, 2 slow) leaves the warp's buffer.  List space is reserved
-    // SCR_RES blocks at a time (one atomic per 32 * SCR_RES entries: every warp of the grid adds to the same three
-    // counters, and same-address atomics are served one after the other by the L2).
-    unsigned long long res_base[3] = {0ull, 0ull, 0ull};
-    unsigned res_left[3] = {0u, 0u, 0u};
-    auto put_block = [&](int which, uint2 e) {
-        if (res_left[which] == 0u) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(s.ctr + (which == 0 ? CTR_FAR : (which == 1 ? CTR_NEAR : CTR_SLOW)), 32ull * SCR_RES);
-            res_base[which] = __shfl_sync(0xffffffffu, base, 0);
-            res_left[which] = SCR_RES;
-        }
-        const unsigned long long pos = res_base[which] + lane;
-        if (which == 0) s.list_far[pos] = e;
-        else if (which == 1) s.list_near[pos] = e;
-        else s.list_near[s.cap - 1 - (long long)pos] = e;
-        res_base[which] += 32ull;
-        res_left[which] -= 1u;
-    };
-    auto flush = [&](int which, bool pad) {
-        uint2 e = s_buf[warp][which][lane];
-        if (pad && lane >= nbuf[which]) e = make_uint2(SCR_NULL, 0u);
-        put_block(which, e);
-        __syncwarp();
-        if (!pad) {
-            if (lane + 32u < nbuf[which]) e = s_buf[warp][which][lane + 32];
-            __syncwarp();
-            if (lane + 32u < nbuf[which]) s_buf[warp][which][lane] = e;
-            nbuf[which] -= 32u;
-        } else {
-            nbuf[which] = 0u;
-        }
-        __syncwarp();
-    };
-    // phase 2 on the first min(32, npend) pending candidates
-    auto process = [&]() {
-        const bool have = lane < npend;
-        int which = -1;
-        uint2 ent = make_uint2(0u, 0u);
-        if (have) {
-            ent = pend[lane];
-            const int i = (int)ent.x, j = (int)ent.y;
-            bool pass = true;
-            int2 ab = make_int2(0, 0);
-            const int2 cd = s.sh_ket[j];
-            if (!s.all_pass) {
-                const double qq = s.Qs_bra[i] * s.Qs_ket[j];
-                ab = s.sh_bra[i];
-                const double *DS = s.DS;
-                const int ns = s.nshell;
-                double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
-                dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
-                                       fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
-                pass = !(qq * dmax < s.tol);
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int j = s.row0 + (int)(blk / ntile);
+        const int c0 = (int)(blk % ntile) * SCR_TILE;
+        if (s.nshards > 1 && (j % s.nshards) != s.shard) continue;
+        const int cstart = s.same_class ? j : 0;
+        if (c0 + SCR_TILE <= cstart) continue;
+        const double qj = s.Qs_ket[j];
+        if (!s.all_pass && s.early) {
+            // dead tile (block-uniform test on the chunk maxima): nothing can pass, so skip the scans, barriers
+            // and atomics altogether — only the candidate count is kept for the statistics
+            bool tile_live = false;
+            for (int ch = c0 >> 8; ch <= ((c0 + SCR_TILE - 1) >> 8); ++ch)
+                if (ch * 256 < s.nbra && !(s.Qmax_bra[ch] * qj * dg4 < s.tol)) tile_live = true;
+            if (!tile_live) {
+                if (threadIdx.x == 0) {
+                    const int lo = max(c0, cstart), hi = min(c0 + SCR_TILE, s.nbra);
+                    if (hi > lo) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)(hi - lo));
+                }
+                continue;
             }
-            if (pass) {
-                kk += (unsigned long long)s.K_bra[i] * (unsigned long long)s.K_ket[j];
-                nq += (s.slice_bra == nullptr || s.slice_bra[i] == 0) ? 1u : 0u;
-                which = 1;
-                if (s.split) {
-                    // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
-                    const bool slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == max(s.bf0[cd.x], s.bf0[cd.y]);
+        }
+        const int2 cd = s.sh_ket[j];
+        const unsigned long long kj = (unsigned long long)s.K_ket[j];
+        // Two phases per warp (128 consecutive columns).  Phase 1: the cheap density-independent bound on all columns,
+        // lane-strided (coalesced), survivors compacted into a per-warp slot array in column order.  Phase 2: the
+        // six-block density test, slicing and list classification on the compacted survivors only.
+        const int wbase = c0 + warp * (SCR_CPT * 32);
+        unsigned bits = 0, sbits = 0, ncand = 0;
+        unsigned nsl[SCR_CPT], fmask[SCR_CPT];       // slices of the pair; which of them are far-field
+        int col[SCR_CPT];
+        unsigned long long kk = 0;
+        const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
+        double4 gk = make_double4(0.0, 0.0, 0.0, 0.0);
+        double qmin = 0.0;
+        if (s.split && s.geo_ket) { gk = s.geo_ket[j]; qmin = s.pmin_ket[j]; }
+        bool warp_live = s.all_pass || !s.early;
+        {
+            const int first = wbase, last = first + SCR_CPT * 32 - 1;
+            for (int wchunk = first >> 8; wchunk <= (last >> 8); ++wchunk)
+                if (wchunk * 256 < s.nbra && !(s.Qmax_bra[wchunk] * qj * dg4 < s.tol)) warp_live = true;
+        }
+        unsigned total = 0;
+#pragma unroll
+        for (int k = 0; k < SCR_CPT; ++k) {
+            const int off = k * 32 + lane;
+            const int i = wbase + off;
+            const bool cand = (i < s.nbra) && (i >= cstart);
+            ncand += cand ? 1u : 0u;            // candidates are counted for the statistics even when the warp exits early
+            bool p1 = cand && warp_live;
+            if (p1 && !s.all_pass) p1 = !(s.Qs_bra[i] * qj * dg4 < s.tol);
+            const unsigned m = __ballot_sync(0xffffffffu, p1);
+            if (p1) s_slot[warp][total + __popc(m & ((1u << lane) - 1u))] = (unsigned short)off;
+            total += __popc(m);
+        }
+        __syncwarp();
+        const unsigned per = (total + 31u) >> 5;      // survivors per lane (<= SCR_CPT)
+        unsigned nent_far = 0, nent_near = 0, nent_slow = 0;
+#pragma unroll
+        for (int k = 0; k < SCR_CPT; ++k) {
+            nsl[k] = 0; fmask[k] = 0;
+            col[k] = 0;
+            const unsigned n = lane * per + k;
+            if ((unsigned)k < per && n < total) {
+                const int i = wbase + s_slot[warp][n];
+                col[k] = i;
+                bool pass = true;
+                int2 ab = make_int2(0, 0);
+                if (!s.all_pass) {
+                    const double qq = s.Qs_bra[i] * qj;
+                    ab = s.sh_bra[i];
+                    const double *DS = s.DS;
+                    const int ns = s.nshell;
+                    double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
+                    dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
+                                           fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
+                    pass = !(qq * dmax < s.tol);
+                }
+                if (pass) {
+                    bits |= 1u << k;
+                    const int kb = s.K_bra[i];
+                    kk += (unsigned long long)kb * kj;
+                    // one list entry per slice of BRA_SLICE bra primitive pairs (direct builds only)
+                    nsl[k] = s.split ? (unsigned)((kb + BRA_SLICE - 1) / BRA_SLICE) : 1u;
+                    bool slow = false;
+                    if (s.split)   // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
+                        slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
                     if (slow) {
-                        which = 2;
-                    } else if (s.geo_bra) {
-                        // far field: every product centre of the bra slice lies in the sphere gb, every one of the ket
-                        // pair in gk, so |PQ| >= d for every primitive quartet; alpha >= pmin qmin / (pmin + qmin)
-                        const double4 gb = s.geo_bra[i], gk = s.geo_ket[j];
-                        const double dx = gb.x - gk.x, dy = gb.y - gk.y, dz = gb.z - gk.z;
-                        const double d = sqrt(dx * dx + dy * dy + dz * dz) - gb.w - gk.w;
-                        const double pm = s.pmin_bra[i], qm = s.pmin_ket[j];
-                        if (d > 0.0 && (pm * qm) * (d * d) >= s.tmax * (pm + qm)) which = 0;
+                        sbits |= 1u << k;
+                        nent_slow += nsl[k];
+                    } else {
+                        unsigned fm = 0;
+                        if (s.split && s.sgeo_bra && nsl[k] <= (unsigned)SCR_MAXSL) {
+                            // far field per slice: every product centre of the slice lies in the sphere gb, every one of
+                            // the ket pair in gk, so |PQ| >= d for every primitive quartet; alpha >= pmin qmin / (pmin + qmin)
+                            const int sb = s.sbase_bra[i];
+                            for (unsigned sl = 0; sl < nsl[k]; ++sl) {
+                                const double4 gb = s.sgeo_bra[sb + sl];
+                                const double dx = gb.x - gk.x, dy = gb.y - gk.y, dz = gb.z - gk.z;
+                                const double d = sqrt(dx * dx + dy * dy + dz * dz) - gb.w - gk.w;
+                                const double pm = s.spmin_bra[sb + sl];
+                                if (d > 0.0 && (pm * qmin) * (d * d) >= s.tmax * (pm + qmin)) fm |= 1u << sl;
+                            }
+                        }
+                        fmask[k] = fm;
+                        nent_far += __popc(fm);
+                        nent_near += nsl[k] - __popc(fm);
                     }
                 }
             }
         }
+        // block-wide exclusive scan of the entry counts: far | near << 21 | slow << 42
+        unsigned long long incl = (unsigned long long)nent_far | ((unsigned long long)nent_near << 21) | ((unsigned long long)nent_slow << 42);
+        const unsigned long long mine = incl;
 #pragma unroll
-        for (int w = 0; w < 3; ++w) {
-            const unsigned m = __ballot_sync(0xffffffffu, which == w);
-            if (which == w) s_buf[warp][w][nbuf[w] + __popc(m & lt)] = ent;
-            nbuf[w] += __popc(m);
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        __syncwarp();
-        // drop the processed candidates from the pending buffer
-        uint2 mv = make_uint2(0u, 0u);
-        if (lane + 32u < npend) mv = pend[lane + 32];
-        __syncwarp();
-        if (lane + 32u < npend) pend[lane] = mv;
-        npend = npend > 32u ? npend - 32u : 0u;
-        __syncwarp();
+        unsigned long long ks = kk;
+        unsigned cs = ncand | ((unsigned)__popc(bits) << 16);      // candidates | shell quartets (<= SCR_CPT each per thread)
 #pragma unroll
-        for (int w = 0; w < 3; ++w)
-            if (nbuf[w] >= 32u) flush(w, false);
-    };
-
-    const int nchunk = (s.nbra + 255) >> 8;
-    for (;;) {
-        int j = 0;
-        if (lane == 0) j = s.row0 + (int)atomicAdd(s.next_row, 1u);
-        j = __shfl_sync(0xffffffffu, j, 0);
-        if (j >= s.row1) break;
-        if (s.nshards > 1 && (j % s.nshards) != s.shard) continue;
-        const double qj = s.Qs_ket[j];
-        // columns are shell pairs in pair order (dense fill): the triangle i >= j is a column range
-        const int cstart = (s.same_class && s.parent_bra == nullptr) ? j : 0;
-        for (int ch = cstart >> 8; ch < nchunk; ++ch) {
-            if (!s.all_pass && s.early && (s.Qmax_bra[ch] * qj * dg4 < s.tol)) {
-                ncand += (lane == 0) ? (unsigned)(min(s.nbra, (ch + 1) << 8) - max(cstart, ch << 8)) : 0u;   // statistics only
-                continue;
-            }
-#pragma unroll 1
-            for (int sub = 0; sub < 8; ++sub) {
-                const int i = (ch << 8) + (sub << 5) + lane;
-                bool cand = (i < s.nbra) && (i >= cstart);
-                if (cand && s.same_class && s.parent_bra != nullptr) cand = s.parent_bra[i] >= j;
-                ncand += cand ? 1u : 0u;
-                bool p1 = cand;
-                if (p1 && !s.all_pass) p1 = !(s.Qs_bra[i] * qj * dg4 < s.tol);
-                const unsigned m = __ballot_sync(0xffffffffu, p1);
-                if (m == 0u) continue;
-                if (p1) pend[npend + __popc(m & lt)] = make_uint2((unsigned)i, (unsigned)j);
-                npend += __popc(m);
-                __syncwarp();
-                if (npend >= 32u) process();
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            ks += __shfl_xor_sync(0xffffffffu, ks, o);
+            cs += __shfl_xor_sync(0xffffffffu, cs, o);
         }
-    }
-    while (npend > 0u) process();
+        if (lane == 31) s_wcnt[warp] = incl;
+        if (lane == 0) { s_wk[warp] = ks; s_wcand[warp] = cs; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tot = 0, tk = 0;
+            unsigned tc = 0, tq = 0;
+            for (int w = 0; w < SCR_THREADS / 32; ++w) {
+                const unsigned long long c = s_wcnt[w];
+                s_wcnt[w] = tot;
+                tot += c;
+                tk += s_wk[w];
+                tc += s_wcand[w] & 0xffffu;
+                tq += s_wcand[w] >> 16;
+            }
+            if (tq) atomicAdd(s.ctr + CTR_NQUART, (unsigned long long)tq);
+            const unsigned tf = (unsigned)(tot & 0x1fffffull), tn = (unsigned)((tot >> 21) & 0x1fffffull), tsl = (unsigned)(tot >> 42);
+            s_base[0] = tf ? atomicAdd(s.ctr + CTR_FAR, (unsigned long long)tf) : 0ull;
+            s_base[1] = tn ? atomicAdd(s.ctr + CTR_NEAR, (unsigned long long)tn) : 0ull;
+            s_base[2] = tsl ? atomicAdd(s.ctr + CTR_SLOW, (unsigned long long)tsl) : 0ull;
+            if (tk) atomicAdd(s.ctr + CTR_PRIMQ, tk);
+            if (tc) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)tc);
+        }
+        __syncthreads();
+        if (bits) {
+            const unsigned long long excl = s_wcnt[warp] + (incl - mine);
+            long long fpos = (long long)(s_base[0] + (excl & 0x1fffffull));
+            long long npos = (long long)(s_base[1] + ((excl >> 21) & 0x1fffffull));
+            long long spos = s.cap - 1 - (long long)(s_base[2] + (excl >> 42));
 #pragma unroll
-    for (int w = 0; w < 3; ++w) {
-        if (nbuf[w] > 0u) flush(w, true);
-        while (res_left[w] > 0u) put_block(w, make_uint2(SCR_NULL, 0u));      // unused part of the last reservation
-    }
-    // statistics: one atomic per counter and warp
-    unsigned long long ks = kk;
-    unsigned cs = ncand, qs = nq;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ks += __shfl_xor_sync(0xffffffffu, ks, o);
-        cs += __shfl_xor_sync(0xffffffffu, cs, o);
-        qs += __shfl_xor_sync(0xffffffffu, qs, o);
-    }
-    if (lane == 0) {
-        if (ks) atomicAdd(s.ctr + CTR_PRIMQ, ks);
-        if (cs) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)cs);
-        if (qs) atomicAdd(s.ctr + CTR_NQUART, (unsigned long long)qs);
+            for (int k = 0; k < SCR_CPT; ++k)
+                if (bits & (1u << k)) {
+                    for (unsigned sl = 0; sl < nsl[k]; ++sl) {
+                        const uint2 ent = make_uint2((unsigned)col[k] | (sl << SLICE_SHIFT), (unsigned)j);
+                        if (sbits & (1u << k)) s.list_near[spos--] = ent;
+                        else if (fmask[k] & (1u << sl)) s.list_far[fpos++] = ent;
+                        else s.list_near[npos++] = ent;
+                    }
+                }
+        }
+        __syncthreads();
     }
 }
 
@@ -864,7 +797,6 @@ __global__ void scatter_dense_kernel(const uint2 *list, const unsigned long long
         const int bb = f % nb;
         const int a = f / nb;
         const uint2 ij = list[e];
-        if (ij.x == LIST_NULL) continue;                               // padding entry
         const PairHdr bh = braH[ij.x], kh = ketH[ij.y];
         const size_t i = bh.bfA + a, j = bh.bfB + bb, k = kh.bfA + c, l = kh.bfB + d;
         // duplicates inside diagonal blocks ((a,b)/(b,a) of one shell, (ab|cd)/(cd|ab) of one pair) are
@@ -937,53 +869,43 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
     }
     CU(cudaGetLastError());
     if (Q_dev) CU(cudaMemcpyAsync(Q_dev, b->Q_dev, N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    CU(cudaStreamSynchronize(st));            // once per geometry: the virtual bra pairs are sorted by these bounds on the host
-    CHK(build_virtual_pairs(b));
     b->have_schwarz = true;
     return MMDB_OK;
 }
 
-// resident warps of the screening kernel: every one may pad each list with up to 31 null entries
-static int screen_grid(const mmdb_basis *b) { return b->nsm * 12; }
-static size_t screen_pad(const mmdb_basis *b, size_t rows) { return std::min<size_t>(rows + SCR_WARPS, (size_t)screen_grid(b) * SCR_WARPS) * 32 * SCR_RES; }
-
 static bool far_enabled(int L)
 {
-    static const int far_maxl = getenv("MMDB_NO_FAR_LIST") ? -1 : (getenv("MMDB_FAR_MAXL") ? atoi(getenv("MMDB_FAR_MAXL")) : 3);
+    // default: off.  Measured on (H2O)32/cc-pVDZ: the far-field kernels run at 17 TFLOP/s (model) against 7 for the near
+    // kernels, but the near list keeps every entry with a single tabulated primitive quartet (44 % of the primitive work,
+    // now fully divergent), so the class times barely move ((ps|ss) 12.5 -> 12.0 ms) while the per-slice classification
+    // adds 2.8 ms of screening.  MMDB_FAR_MAXL=1..3 switches the lists on up to that total angular momentum.
+    const int far_maxl = getenv("MMDB_NO_FAR_LIST") ? -1 : std::min(FAR_MAXL, getenv("MMDB_FAR_MAXL") ? atoi(getenv("MMDB_FAR_MAXL")) : -1);      // read per call: a run can switch
     return L <= far_maxl;
 }
 
-// use_vp: columns are the bra class's virtual pairs (direct builds); otherwise its shell pairs (dense fill)
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
                       bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, uint2 *list_far,
-                      uint2 *list_near, bool use_vp, cudaStream_t st)
+                      uint2 *list_near, cudaStream_t st)
 {
     ScreenArgs s;
     std::memset(&s, 0, sizeof(s));
-    if (use_vp) {
-        s.Qs_bra = B.vQs_dev; s.Qmax_bra = B.vQmax_dev; s.sh_bra = B.vsh_dev; s.K_bra = B.vK_dev; s.nbra = B.nvp;
-        s.parent_bra = B.vparent_dev; s.slice_bra = B.vslice_dev; s.geo_bra = B.vgeo_dev; s.pmin_bra = B.vpmin_dev;
-        s.geo_ket = K.geo_dev; s.pmin_ket = K.pmin_dev;
-    } else {
-        s.Qs_bra = B.Qs_dev; s.Qmax_bra = B.Qmax_dev; s.sh_bra = B.sh_dev; s.K_bra = B.K_dev; s.nbra = B.npairs;
+    s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.Qmax_bra = B.Qmax_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
+    s.K_bra = B.K_dev; s.K_ket = K.K_dev;
+    // The far-field list pays where Boys + R dominate a primitive quartet (L <= 3); above that the extra launch per
+    // class pair costs more than the table branch it saves.  MMDB_NO_FAR_LIST / MMDB_FAR_MAXL: A/B switches.
+    if (split && far_enabled(B.la + B.lb + K.la + K.lb)) {
+        s.sbase_bra = B.sbase_dev; s.sgeo_bra = B.sgeo_dev; s.spmin_bra = B.spmin_dev; s.geo_ket = K.geo_dev; s.pmin_ket = K.pmin_dev;
     }
-    s.Qs_ket = K.Qs_dev; s.sh_ket = K.sh_dev; s.K_ket = K.K_dev;
     s.tmax = (double)boys_tmax_i(B.la + B.lb + K.la + K.lb) + 0.5;     // margin: rounding of the bounding-sphere distances
-    s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
+    s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
     s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
     s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list_far = list_far; s.list_near = list_near;
     s.ctr = b->ctr_dev + CTR_PER_LAUNCH * slot;
     s.early = getenv("MMDB_SCREEN_NO_EARLY_EXIT") ? 0 : 1;
     s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
-    // The far-field list pays where Boys + R dominate a primitive quartet (L <= 3); above that the two extra launches per
-    // class pair cost more than the table branch they save.  MMDB_NO_FAR_LIST / MMDB_FAR_MAXL: A/B switches.
-    if (!far_enabled(B.la + B.lb + K.la + K.lb)) s.geo_bra = nullptr;
-    s.next_row = reinterpret_cast<unsigned *>(s.ctr + CTR_ROW);        // zeroed with the counters
-    // enough warps to fill the GPU on the big class pairs, but at least ~64k candidates per warp: every warp leaves one
-    // partly filled 32-entry block per list behind, and an ERI warp that gets such a block runs with idle lanes
-    const long long cand = (long long)(row1 - row0) * s.nbra / (nshards > 0 ? nshards : 1);
-    const long long want = std::max<long long>(1, cand / 65536 / SCR_WARPS);
-    const int grid = (int)std::min<long long>(std::min<long long>(want, ((long long)(row1 - row0) + SCR_WARPS - 1) / SCR_WARPS), (long long)screen_grid(b));
+    const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
+    const long long nblk = (long long)(row1 - row0) * ntile;
+    const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 32);
     if (grid > 0) screen_kernel<<<grid, SCR_THREADS, 0, st>>>(s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MMDB_ERR_CUDA, std::string("screen kernel: ") + cudaGetErrorString(e));
@@ -1008,14 +930,14 @@ extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
             const size_t nfn = (size_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
-            size_t rows_per = std::max<size_t>(1, std::min(LIST_CAP, SCRATCH_CAP / nfn) / ((size_t)B.npairs + 32));
+            size_t rows_per = std::max<size_t>(1, std::min(LIST_CAP, SCRATCH_CAP / nfn) / (size_t)B.npairs);
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                const size_t cap = (size_t)(row1 - row0) * B.npairs + screen_pad(b, (size_t)(row1 - row0));
+                const size_t cap = (size_t)(row1 - row0) * B.npairs;
                 CHK(ensure_list(b, cap));
                 CHK(ensure_scratch(b, cap * nfn));
                 if ((slot + 1) * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_eri_dense: counter slots exhausted");
-                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, b->list_dev, b->list_dev, false, st));
+                CHK(run_screen(b, B, K, cb == ck, row0, row1, 0, 1, true, -1.0, slot, false, false, (long long)cap, b->list_dev, b->list_dev, st));
                 EriArgs a;
                 std::memset(&a, 0, sizeof(a));
                 a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
@@ -1066,11 +988,11 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             PairClass &B = b->pc[cb], &K = b->pc[ck];
             if (B.npairs == 0 || K.npairs == 0) continue;
             // rows of this shard only count towards the list capacity
-            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.nvp * (size_t)nshards);
+            size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.slice_entries * (size_t)nshards);
             const bool small = !timing && (size_t)B.npairs * K.npairs / nshards <= AUX_MAX_CANDIDATES;
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
-                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.nvp + 2 * screen_pad(b, (size_t)(row1 - row0));   // room for every virtual pair + the padding of the flush blocks (near and slow share a buffer)
+                const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.slice_entries;   // room for every slice
                 tasks.push_back(Task{cb, ck, row0, row1, cap, small});
                 (small ? cap_aux : cap_main) = std::max(small ? cap_aux : cap_main, cap);
             }
@@ -1140,7 +1062,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             uint2 *list_far = list, *list_near = list + cap_region[t.aux ? 1 : 0];
             CHK(run_screen(b, B, K, t.cb == t.ck, t.row0, t.row1, shard, nshards, false, tol, slot, true,
                            dP_im_dev != nullptr || (flags & 2) != 0,
-                           (long long)t.cap, list_far, list_near, true, s_scr));
+                           (long long)t.cap, list_far, list_near, s_scr));
             if (piped) {
                 CU(cudaEventRecord(ev_ready, ss));
                 CU(cudaStreamWaitEvent(st, ev_ready, 0));
@@ -1148,8 +1070,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             if (timing) CU(cudaEventRecord(ln.em, s1));
             EriArgs a;
             std::memset(&a, 0, sizeof(a));
-            // bra side = the class's virtual pairs (slices of <= BRA_SLICE primitive pairs)
-            a.braH = B.vhdr_dev; a.braP = B.prim_dev; a.braS = B.vsoa_dev; a.braRow = B.vrow_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
+            a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
             a.same_class = (t.cb == t.ck);
             a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
             a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
@@ -1179,7 +1100,8 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         CU(cudaMemcpyAsync(ctr.data(), b->ctr_dev, sizeof(unsigned long long) * CTR_PER_LAUNCH * slot, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof(*stats));
-        stats->launches = 2 + 4 * (int64_t)launches.size();
+        stats->launches = 2;                                   // dabs + dshell, then per task: screen + far? + near + slow
+        for (auto &ln : launches) stats->launches += 3 + (far_enabled(b->pc[ln.cb].la + b->pc[ln.cb].lb + b->pc[ln.ck].la + b->pc[ln.ck].lb) ? 1 : 0);
         for (auto &ln : launches) {
             const PairClass &B = b->pc[ln.cb], &K = b->pc[ln.ck];
             const int64_t nq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_NQUART];
@@ -1282,7 +1204,6 @@ extern "C" int mmdb_set_schwarz_host(mmdb_basis *b, const double *Q_tri)
     }
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
-    CHK(build_virtual_pairs(b));
     b->have_schwarz = true;
     return MMDB_OK;
 }

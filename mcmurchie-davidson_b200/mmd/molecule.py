@@ -92,6 +92,12 @@ class Molecule(SCF):
         for atom in self.atoms:
             atom_first = len(self.bfs)
             for momentum, prims in self.basis_data[atom.charge]:
+                if str(momentum) not in ("S", "P", "D"):
+                    # fail here, with the reason, rather than deep inside the engine (the reference's general-L recursion
+                    # accepts F shells; the device kernels are instantiated for (ss|ss) ... (dd|dd))
+                    raise NotImplementedError("basis '%s' has %s functions on Z=%d: the B200 engine covers s, p and d shells "
+                                              "((ss|ss) ... (dd|dd) class kernels; f-type Hermite tables exist only inside the "
+                                              "gradient kernels)" % (self.basis_name, momentum, atom.charge))
                 exps = np.asarray([e for e, _ in prims])
                 coefs = np.asarray([c for _, c in prims])
                 for lmn in self.momentum2shell(momentum):

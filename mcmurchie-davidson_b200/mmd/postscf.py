@@ -8,6 +8,9 @@ from itertools import product
 import numpy as np
 
 
+EAGER_DOUBLE_BAR_BYTES = 512 * 1024 * 1024       # N <= 38: mol.double_bar is built in ao2mo like the reference does
+
+
 class PostSCF(object):
     def __init__(self, mol):
         self.mol = mol
@@ -39,12 +42,17 @@ class PostSCF(object):
             self.mol.single_bar = np.einsum("pQRS,pP->PQRS", t, Cc, optimize=True)
         self.mol.norb = self.mol.nbasis * 2
         self._spin = np.eye(2)
-        # spin-orbital quantities are O((2N)^4) and only needed for spin_orbital=True: built lazily
+        # The reference sets mol.double_bar right here (mmd/postscf.py:34-35) — code that reads it after PostSCF(mol) keeps
+        # working for the sizes the reference itself can handle; beyond that the 16 (2N)^4-byte spin-orbital tensor
+        # is built on first use instead (spin_orbital=True), since the spatial-orbital MP2 never needs it.
+        self.mol.double_bar = None
+        if 16.0 * (2.0 * self.mol.nbasis) ** 4 <= EAGER_DOUBLE_BAR_BYTES:
+            self._ensure_double_bar()
         self.mol.fs = np.kron(np.diag(self.mol.MO), self._spin)
         self.mol.Hp = np.kron(np.einsum("uj,vi,uv", C, C, self.mol.Core).real, self._spin)
 
     def _ensure_double_bar(self):
-        if getattr(self.mol, "double_bar", None) is None or not hasattr(self.mol, "double_bar"):
+        if getattr(self.mol, "double_bar", None) is None:
             block = np.kron(np.kron(self.mol.single_bar, self._spin).transpose(), self._spin).real
             self.mol.double_bar = block.transpose(0, 2, 1, 3) - block.transpose(0, 2, 3, 1)
 
