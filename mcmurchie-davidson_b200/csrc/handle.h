@@ -77,12 +77,14 @@ struct mmdb_basis {
     int nctr = 0;
     cudaStream_t aux_stream = nullptr;            // small class pairs run here, concurrently with the big ones
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t main2_stream = nullptr;          // odd main-queue class pairs run here: their grids fill the SMs the previous pair's tail vacates
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaStream_t scr_stream = nullptr;            // screening of the NEXT class pair runs here, one task ahead of the ERI kernels
     cudaEvent_t ev_fork_scr = nullptr;
     std::vector<cudaEvent_t> ev_pool;             // per-task "list ready" / "list consumed" events of the screening pipeline
     double *scratch_dev = nullptr;
     size_t scratch_cap = 0;   // doubles
-    double *eri_scratch_dev = nullptr;            // [2 regions][54 * nsm * 2048] contracted-block columns of the scratch_out classes (main / aux stream)
+    double *eri_scratch_dev = nullptr;            // [3 regions][54 * nsm * 2048] contracted-block columns of the scratch_out classes (main / aux / second main stream)
     double *stage_host = nullptr, *stage_dev = nullptr;   // mmdb_formPT_host staging: 4 planes of N^2 doubles each (page-locked / device)
     size_t stage_n = 0;
 };

