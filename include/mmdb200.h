@@ -108,6 +108,8 @@ typedef struct {
     float class_screen_ms[MMDB_NCLASS_PAIR * MMDB_NCLASS_PAIR]; /* screening kernel time per class (flags bit0)     */
     int64_t far_entries;      /* list entries (virtual bra pair, ket pair) on the far-field lists: every primitive quartet asymptotic */
     int64_t near_entries;     /* block-digestible list entries with at least one primitive quartet in the tabulated Boys range */
+    int64_t exec_prim_quartets; /* primitive quartets actually evaluated: generally contracted s shells share theirs, so this is
+                                   below prim_quartets (which, like quartets, is counted in the reference's own shells) unless flags bit2 */
 } mmdb_fock_stats;
 
 /* Direct Fock build (cython/fock.pyx:13-87): G += contributions of every canonical basis-function
@@ -122,6 +124,10 @@ typedef struct {
  *        bit1 = DETERMINISTIC accumulation: contributions are rounded to multiples of 2^-50 and added with 64-bit
  *               integer atomics, so G is bitwise reproducible for any schedule / shard count.  G then holds scaled
  *               integers: sum the shards as int64 and finish with mmdb_fixed_to_double.
+ *        bit2 = plain shell classes only.  By default generally contracted s shells (two consecutive s shells on one
+ *               centre over the same primitives, e.g. cc-pVDZ) are evaluated as ONE two-component pseudo-shell so their
+ *               primitive integrals are computed once; G is the same, the shell-level screen is a superset.  With bit2
+ *               every reference shell is its own shell: the statistics are then exactly the reference's shell quartets.
  * Streams: the call is asynchronous with respect to the host and ordered on `stream` — everything enqueued on
  * `stream` after it sees the complete G.  Internally it forks onto two handle-owned streams (small class pairs;
  * the screening pipeline that runs one class pair ahead of the ERI kernels) and joins them back with events,

@@ -57,6 +57,28 @@ __host__ __device__ constexpr double comp_scale(int l, int c)
     return s;
 }
 
+// ------------------------------------------------------------------------------------------
+// Shell TYPE codes of the class kernels.  0, 1, 2 = s, p, d shells.  3 = "S2": a generally contracted s pseudo-shell —
+// TWO s-type contractions over ONE primitive set on one centre (cc-pVDZ's first two s functions of every heavy atom),
+// i.e. two consecutive basis functions that share every primitive integral and differ only in their contraction
+// coefficients.  A pair that contains an S2 shell keeps the geometric part of its pair coefficient in PrimPair::cc
+// and one WEIGHT c_a^(i) c_b^(j) per component pair beside it; the kernels evaluate each primitive quartet once and
+// apply the weights where the Hermite -> Cartesian coefficients are applied.  (The reference evaluates every
+// contracted function quartet from scratch, cython/twoe.pyx:36-50.)
+// ------------------------------------------------------------------------------------------
+constexpr int SH_S2 = 3;
+__host__ __device__ constexpr int am_of(int t) { return t == SH_S2 ? 0 : t; }
+__host__ __device__ constexpr int ncomp(int t) { return t == SH_S2 ? 2 : ncart(t); }
+__host__ __device__ constexpr int comp_pow(int t, int c, int dim) { return t == SH_S2 ? 0 : cart_pow(t, c, dim); }
+__host__ __device__ constexpr double cscale(int t, int c) { return t == SH_S2 ? 1.0 : comp_scale(t, c); }
+// weights of a pair of shell types: one per component pair of its S2 members
+__host__ __device__ constexpr int nwgt(int ta, int tb) { return (ta == SH_S2 ? 2 : 1) * (tb == SH_S2 ? 2 : 1); }
+__host__ __device__ constexpr int widx(int ta, int tb, int a, int b)
+{
+    return (ta == SH_S2 ? a : 0) * (tb == SH_S2 ? 2 : 1) + (tb == SH_S2 ? b : 0);
+}
+constexpr int MAX_WGT = 4;
+
 template <int I, int N, class F>
 __device__ __forceinline__ void sfor(F &&f)
 {
@@ -134,7 +156,33 @@ struct BraSrc {
     const long long *row;
     long long N;
     unsigned pair;
+    const double *W;       // weights of the pairs with an S2 member: [MAX_WGT fields][N], same rows as S (or nullptr)
 };
+template <int NW>
+__device__ __forceinline__ void ld_wgt_soa(const BraSrc &src, int k, double (&w)[NW])
+{
+    if constexpr (NW > 1) {
+        const double *q = src.W + (__ldg(src.row + k) + (long long)src.pair);
+#pragma unroll
+        for (int x = 0; x < NW; ++x) w[x] = __ldg(q + x * src.N);
+    } else {
+        w[0] = 1.0;
+    }
+}
+// ket side: weights of primitive pair i at W[i * MAX_WGT ..] (warp-uniform address: broadcast loads)
+template <int NW>
+__device__ __forceinline__ void ld_wgt(const double *__restrict__ W, long long i, double (&w)[NW])
+{
+    if constexpr (NW == 4) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(W + i * MAX_WGT)), b = __ldg(reinterpret_cast<const double2 *>(W + i * MAX_WGT) + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+    } else if constexpr (NW == 2) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(W + i * MAX_WGT));
+        w[0] = a.x; w[1] = a.y;
+    } else {
+        w[0] = 1.0;
+    }
+}
 __device__ __forceinline__ PrimPair ld_prim_soa(const BraSrc &src, int k)
 {
     const double *q = src.S + (__ldg(src.row + k) + (long long)src.pair);
@@ -437,11 +485,18 @@ __device__ __noinline__ void prim_R_smem(double *base, int stride, double pb, do
     prim_R<L, FAR>(R, pb, pk, ccb, cck, X, Y, Z, boys_tab);
 }
 
+// one ket primitive pair with the weights of its component pairs (pairs with an S2 member; unused otherwise)
+template <int NW>
+struct KetPrimT {
+    PrimPair p;
+    double w[NW];
+};
+
 // ---- compile-time layout of the signed ket coefficient products of one chunk (R-major ket transform) -------------------
 template <int LC, int LD>
 __host__ __device__ constexpr int ket_box(int cd, int dim)
 {
-    return cart_pow(LC, cd / ncart(LD), dim) + cart_pow(LD, cd % ncart(LD), dim);
+    return comp_pow(LC, cd / ncomp(LD), dim) + comp_pow(LD, cd % ncomp(LD), dim);
 }
 template <int LC, int LD, int CD0>
 __host__ __device__ constexpr int ket_coef_off(int cdi, int tau, int nu, int phi)
@@ -484,13 +539,15 @@ __host__ __device__ constexpr bool ket_uses_R(int KT, int KU, int KV)
 // one, so Boys + R + the bra E table are built a third as often and the digestion shares its bra-block loads.
 template <int LA, int LB, int LC, int LD, int CD0, int NCDC, bool RSMEM, bool SERIAL_CHUNKS, bool FAR = false, bool SCR_OUT = false>
 __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraSrc &bsrc,
-                                                   const PairHdr &kh, const PrimPair *__restrict__ kp,
+                                                   const PairHdr &kh, const PrimPair *__restrict__ kp, const double *__restrict__ kw,
                                                    const double *__restrict__ boys_tab, double *r_smem, int r_stride,
-                                                   int ib0, int ib1, double (&out)[ncart(LA) * ncart(LB) * NCDC],
+                                                   int ib0, int ib1, double (&out)[ncomp(LA) * ncomp(LB) * NCDC],
                                                    double *__restrict__ outg = nullptr, long long ostride = 0)
 {
-    constexpr int LBRA = LA + LB, LKET = LC + LD, L = LBRA + LKET;
-    constexpr int NA = ncart(LA), NB = ncart(LB), ND = ncart(LD);
+    // LA..LD are shell TYPE codes (am_of: 3 = S2 is an s shell with two components)
+    constexpr int LBRA = am_of(LA) + am_of(LB), LKET = am_of(LC) + am_of(LD), L = LBRA + LKET;
+    constexpr int NA = ncomp(LA), NB = ncomp(LB), ND = ncomp(LD);
+    constexpr int NWB = nwgt(LA, LB), NWK = nwgt(LC, LD);
     constexpr int NAB = NA * NB;
     constexpr int NHB = nherm(LBRA);
 
@@ -499,18 +556,27 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
         for (int x = 0; x < NAB * NCDC; ++x) out[x] = 0.0;
     }
 
+    using KetPrim = KetPrimT<NWK>;
+    auto ld_kp = [&](int i) -> KetPrim {
+        KetPrim r;
+        r.p = ld_prim(kp + i);
+        ld_wgt<NWK>(kw, (long long)i, r.w);
+        return r;
+    };
     for (int ib = ib0; ib < ib1; ++ib) {       // [ib0,ib1): this entry's slice of the bra primitive pairs
         const PrimPair b = ld_prim_soa(bsrc, ib);
+        double wb[NWB];
+        ld_wgt_soa<NWB>(bsrc, ib, wb);
         double G[NHB * NCDC];
 #pragma unroll
         for (int x = 0; x < NHB * NCDC; ++x) G[x] = 0.0;
 
-        auto ket_transform = [&](const auto &R, const PrimPair &k) {
-            ETab<LC, LD> Ek;
+        auto ket_transform = [&](const auto &R, const PrimPair &k, const double *wk) {      // (an array-reference parameter here crashes cudafe++ 12.9)
+            ETab<am_of(LC), am_of(LD)> Ek;
             {
                 const double QC[3] = {k.PAx, k.PAy, k.PAz};
                 const double QD[3] = {k.PAx + kh.ABx, k.PAy + kh.ABy, k.PAz + kh.ABz};
-                build_E<LC, LD>(Ek, QC, QD, 0.5 / k.p);
+                build_E<am_of(LC), am_of(LD)>(Ek, QC, QD, 0.5 / k.p);
             }
             // ket Hermite -> Cartesian:  G[tuv][cd] += (-1)^(tau+nu+phi) E^cd_tau E^cd_nu E^cd_phi R[t+tau,u+nu,v+phi]
             if constexpr (RSMEM) {
@@ -524,16 +590,17 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                     constexpr int cdi = decltype(CDI)::value;
                     constexpr int cd = CD0 + cdi;
                     constexpr int c = cd / ND, d = cd % ND;
-                    constexpr int ex = cart_pow(LC, c, 0) + cart_pow(LD, d, 0), ey = cart_pow(LC, c, 1) + cart_pow(LD, d, 1),
-                                  ez = cart_pow(LC, c, 2) + cart_pow(LD, d, 2);
+                    constexpr int ex = comp_pow(LC, c, 0) + comp_pow(LD, d, 0), ey = comp_pow(LC, c, 1) + comp_pow(LD, d, 1),
+                                  ez = comp_pow(LC, c, 2) + comp_pow(LD, d, 2);
                     sfor<0, ex + 1>([&](auto TAU) {
                         constexpr int tau = decltype(TAU)::value;
                         sfor<0, ey + 1>([&](auto NU) {
                             constexpr int nu = decltype(NU)::value;
-                            const double exy = Ek.v[0][cart_pow(LC, c, 0)][cart_pow(LD, d, 0)][tau] * Ek.v[1][cart_pow(LC, c, 1)][cart_pow(LD, d, 1)][nu];
+                            const double exy = Ek.v[0][comp_pow(LC, c, 0)][comp_pow(LD, d, 0)][tau] * Ek.v[1][comp_pow(LC, c, 1)][comp_pow(LD, d, 1)][nu];
                             sfor<0, ez + 1>([&](auto PHI) {
                                 constexpr int phi = decltype(PHI)::value;
-                                double coef = exy * Ek.v[2][cart_pow(LC, c, 2)][cart_pow(LD, d, 2)][phi];
+                                double coef = exy * Ek.v[2][comp_pow(LC, c, 2)][comp_pow(LD, d, 2)][phi];
+                                if constexpr (NWK > 1) coef *= wk[widx(LC, LD, c, d)];
                                 if constexpr ((tau + nu + phi) & 1) coef = -coef;
                                 co[ket_coef_off<LC, LD, CD0>(cdi, tau, nu, phi)] = coef;
                             });
@@ -552,8 +619,8 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                                     constexpr int cdi = decltype(CDI)::value;
                                     constexpr int cd = CD0 + cdi;
                                     constexpr int c = cd / ND, d = cd % ND;
-                                    constexpr int ex = cart_pow(LC, c, 0) + cart_pow(LD, d, 0), ey = cart_pow(LC, c, 1) + cart_pow(LD, d, 1),
-                                                  ez = cart_pow(LC, c, 2) + cart_pow(LD, d, 2);
+                                    constexpr int ex = comp_pow(LC, c, 0) + comp_pow(LD, d, 0), ey = comp_pow(LC, c, 1) + comp_pow(LD, d, 1),
+                                                  ez = comp_pow(LC, c, 2) + comp_pow(LD, d, 2);
                                     sfor<0, (KT < ex ? KT : ex) + 1>([&](auto TAU) {
                                         constexpr int tau = decltype(TAU)::value;
                                         sfor<0, (KU < ey ? KU : ey) + 1>([&](auto NU) {
@@ -577,8 +644,8 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                 constexpr int cdi = decltype(CDI)::value;
                 constexpr int cd = CD0 + cdi;
                 constexpr int c = cd / ND, d = cd % ND;
-                constexpr int cx = cart_pow(LC, c, 0), cy = cart_pow(LC, c, 1), cz = cart_pow(LC, c, 2);
-                constexpr int dx = cart_pow(LD, d, 0), dy = cart_pow(LD, d, 1), dz = cart_pow(LD, d, 2);
+                constexpr int cx = comp_pow(LC, c, 0), cy = comp_pow(LC, c, 1), cz = comp_pow(LC, c, 2);
+                constexpr int dx = comp_pow(LD, d, 0), dy = comp_pow(LD, d, 1), dz = comp_pow(LD, d, 2);
                 sfor<0, cx + dx + 1>([&](auto TAU) {
                     constexpr int tau = decltype(TAU)::value;
                     sfor<0, cy + dy + 1>([&](auto NU) {
@@ -587,6 +654,7 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                         sfor<0, cz + dz + 1>([&](auto PHI) {
                             constexpr int phi = decltype(PHI)::value;
                             double coef = exy * Ek.v[2][cz][dz][phi];
+                            if constexpr (NWK > 1) coef *= wk[widx(LC, LD, c, d)];
                             if constexpr ((tau + nu + phi) & 1) coef = -coef;
                             sfor<0, LBRA + 1>([&](auto TT) {
                                 constexpr int t = decltype(TT)::value;
@@ -605,7 +673,8 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
             });
             }
         };
-        auto ket_body = [&](const PrimPair &k) {
+        auto ket_body = [&](const KetPrim &kq) {
+            const PrimPair &k = kq.p;
             const double X = b.Px - k.Px, Y = b.Py - k.Py, Z = b.Pz - k.Pz;
             RStore<L, RSMEM> R;
             if constexpr (RSMEM) {
@@ -618,14 +687,15 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
             } else {
                 prim_R<L, FAR>(R, b.p, k.p, b.cc, k.cc, X, Y, Z, boys_tab);
             }
-            ket_transform(R, k);
+            ket_transform(R, k, kq.w);
         };
         // Two ket primitives at once (L <= 1 only).  These kernels are latency-bound: ~5 warps per scheduler, and
         // one primitive quartet is essentially ONE dependent chain (|PQ|^2 -> rsqrt -> F_m -> R -> G), so the
         // FP64 pipe idles between dependent instructions.  When both primitive quartets are on the branch-free
         // asymptotic path for every converged lane, the two chains are emitted in one basic block and the
         // compiler interleaves them; otherwise the two bodies run one after the other as before.
-        auto ket_body2 = [&](const PrimPair &ka, const PrimPair &kc) {
+        auto ket_body2 = [&](const KetPrim &kqa, const KetPrim &kqc) {
+            const PrimPair &ka = kqa.p, &kc = kqc.p;
             const double Xa = b.Px - ka.Px, Ya = b.Py - ka.Py, Za = b.Pz - ka.Pz;
             const double Xc = b.Px - kc.Px, Yc = b.Py - kc.Py, Zc = b.Pz - kc.Pz;
             const double R2a = Xa * Xa + Ya * Ya + Za * Za, R2c = Xc * Xc + Yc * Yc + Zc * Zc;
@@ -641,11 +711,11 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                 RStore<L, false> Ra, Rc;
                 prim_R_asym<L>(Ra, b.cc * ka.cc, R2a, Xa, Ya, Za);
                 prim_R_asym<L>(Rc, b.cc * kc.cc, R2c, Xc, Yc, Zc);
-                ket_transform(Ra, ka);
-                ket_transform(Rc, kc);
+                ket_transform(Ra, ka, kqa.w);
+                ket_transform(Rc, kc, kqc.w);
             } else {
-                ket_body(ka);
-                ket_body(kc);
+                ket_body(kqa);
+                ket_body(kqc);
             }
         };
         // The next ket primitive pair is loaded while the current one is consumed.  The light classes
@@ -653,14 +723,14 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
         // the 16 register copies were a fifth of their inner loop; the heavy classes keep one copy of
         // the (large) loop body.
         if constexpr (L <= 2) {
-            PrimPair k0 = ld_prim(kp + kh.poff), k1 = k0;
+            KetPrim k0 = ld_kp(kh.poff), k1 = k0;
             for (int ik = 0; ik < kh.pnum; ik += 2) {
                 const bool two = ik + 1 < kh.pnum;
-                if (two) k1 = ld_prim(kp + kh.poff + ik + 1);
+                if (two) k1 = ld_kp(kh.poff + ik + 1);
                 if constexpr (L <= 1 && !RSMEM) {
                     if (two) {
-                        const PrimPair ka = k0;
-                        if (ik + 2 < kh.pnum) k0 = ld_prim(kp + kh.poff + ik + 2);
+                        const KetPrim ka = k0;
+                        if (ik + 2 < kh.pnum) k0 = ld_kp(kh.poff + ik + 2);
                         ket_body2(ka, k1);
                     } else {
                         ket_body(k0);
@@ -668,32 +738,32 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                 } else {
                     ket_body(k0);
                     if (two) {
-                        if (ik + 2 < kh.pnum) k0 = ld_prim(kp + kh.poff + ik + 2);
+                        if (ik + 2 < kh.pnum) k0 = ld_kp(kh.poff + ik + 2);
                         ket_body(k1);
                     }
                 }
             }
         } else {
-            PrimPair k_next = ld_prim(kp + kh.poff);
+            KetPrim k_next = ld_kp(kh.poff);
             for (int ik = 0; ik < kh.pnum; ++ik) {
-                const PrimPair k = k_next;
-                if (ik + 1 < kh.pnum) k_next = ld_prim(kp + kh.poff + ik + 1);
+                const KetPrim k = k_next;
+                if (ik + 1 < kh.pnum) k_next = ld_kp(kh.poff + ik + 1);
                 ket_body(k);
             }
         }
         // bra Hermite -> Cartesian:  out[ab][cd] += E^ab_t E^ab_u E^ab_v G[tuv][cd]
         // (the bra E table is built here, after the ket primitives, so it is not live across the ket loop)
-        ETab<LA, LB> Eb;
+        ETab<am_of(LA), am_of(LB)> Eb;
         {
             const double PA[3] = {b.PAx, b.PAy, b.PAz};
             const double PB[3] = {b.PAx + bh.ABx, b.PAy + bh.ABy, b.PAz + bh.ABz};
-            build_E<LA, LB>(Eb, PA, PB, 0.5 / b.p);
+            build_E<am_of(LA), am_of(LB)>(Eb, PA, PB, 0.5 / b.p);
         }
         sfor<0, NAB>([&](auto ABI) {
             constexpr int ab = decltype(ABI)::value;
             constexpr int a = ab / NB, bb = ab % NB;
-            constexpr int ax = cart_pow(LA, a, 0), ay = cart_pow(LA, a, 1), az = cart_pow(LA, a, 2);
-            constexpr int bx = cart_pow(LB, bb, 0), by = cart_pow(LB, bb, 1), bz = cart_pow(LB, bb, 2);
+            constexpr int ax = comp_pow(LA, a, 0), ay = comp_pow(LA, a, 1), az = comp_pow(LA, a, 2);
+            constexpr int bx = comp_pow(LB, bb, 0), by = comp_pow(LB, bb, 1), bz = comp_pow(LB, bb, 2);
             double acc[NCDC];
             if constexpr (SCR_OUT) {
 #pragma unroll
@@ -706,7 +776,8 @@ __device__ __forceinline__ void eval_quartet_chunk(const PairHdr &bh, const BraS
                     const double exy = Eb.v[0][ax][bx][t] * Eb.v[1][ay][by][u];
                     sfor<0, az + bz + 1>([&](auto VV) {
                         constexpr int v = decltype(VV)::value;
-                        const double coef = exy * Eb.v[2][az][bz][v];
+                        double coef = exy * Eb.v[2][az][bz][v];
+                        if constexpr (NWB > 1) coef *= wb[widx(LA, LB, a, bb)];
 #pragma unroll
                         for (int cdi = 0; cdi < NCDC; ++cdi) {
                             if constexpr (SCR_OUT) acc[cdi] = fma(coef, G[hidx(t, u, v) * NCDC + cdi], acc[cdi]);
@@ -797,8 +868,10 @@ struct EriArgs {
     const double *braS;           // structure-of-arrays copy of the bra primitive pairs (class kernels), see BraSrc
     const long long *braRow;
     long long braN;
+    const double *braW;           // weights of bra pairs with an S2 member: [MAX_WGT][braN], rows as braS (or nullptr)
     const PairHdr *ketH;
     const PrimPair *ketP;
+    const double *ketW;           // weights of ket pairs with an S2 member: [nprimpairs][MAX_WGT] (or nullptr)
     const uint2 *list;            // (bra pair, ket pair) per entry; entry e lives at list[e * list_step]
     long long list_step;          // +1: front-to-back (fast-path list), -1: back-to-front (slow-path list)
     const unsigned long long *count_dev;   // number of entries (device) or nullptr -> use n

@@ -27,9 +27,15 @@ static inline int fail(int code, const std::string &msg)
     } while (0)
 
 struct ShellH {
-    int am, nprim, poff, bf0;
+    int am, nprim, poff, bf0;      // am: shell TYPE code (0 s, 1 p, 2 d; 3 = S2 pseudo-shell in the grouped list, core.cuh)
     double x, y, z;
+    int poff2 = 0;                 // S2: offset of the SECOND contraction's coefficients (exponents are those at poff)
+    int id = 0;                    // shell id the pair headers carry (index into the list's bf0 / density-block tables)
 };
+
+// pair classes of the GROUPED shell list of the direct Fock build: the six plain ones + (S2 s), (S2 p), (S2 S2).
+// An (S2, d) pair is expanded into its two plain (d s) pairs.
+constexpr int MMDB_NCLASS_GC = 9;
 
 struct PairClass {
     int la = 0, lb = 0;
@@ -54,6 +60,9 @@ struct PairClass {
     double *Qs_dev = nullptr;   // [npairs]
     double *Qmax_dev = nullptr; // [ceil(npairs/256)] maxima of Qs over 256-pair chunks (screening early-exit)
     int *K_dev = nullptr;       // [npairs] primitive pairs per shell pair
+    int *Kref_dev = nullptr;    // [npairs] statistics: primitive pairs summed over the member contractions | members << 24
+    double *wgt_dev = nullptr;      // pairs with an S2 member: [nprimpairs][MAX_WGT] contraction weights (ket side)
+    double *wgt_soa_dev = nullptr;  // the same as [MAX_WGT][nprimpairs] in the rows of prim_soa_dev (bra side)
     int2 *sh_dev = nullptr;     // [npairs] (shA, shB)
 };
 
@@ -64,6 +73,13 @@ struct mmdb_basis {
     std::vector<ShellH> sh;
     std::vector<double> exps, coefs;
     PairClass pc[MMDB_NCLASS_PAIR];
+    // grouped shell list (S2 pseudo-shells) and its pair classes: what the direct Fock build runs on
+    std::vector<ShellH> shg;
+    int nshellg = 0;
+    bool have_gc = false;                         // the list contains at least one S2 pseudo-shell
+    PairClass pcg[MMDB_NCLASS_GC];
+    int *shg_bf0_dev = nullptr, *shg_nf_dev = nullptr;
+    double *DSg_dev = nullptr;                    // (nshellg,nshellg)
     double *boys_dev[mmdb::BOYS_MAXL + 1] = {nullptr};
     int *sh_bf0_dev = nullptr, *sh_nf_dev = nullptr;
     double *Q_dev = nullptr, *SQ_dev = nullptr;   // (N,N)

@@ -1,0 +1,7 @@
+// explicit instantiations of the class kernels with an S2 pseudo-shell (shell type code 3, core.cuh)
+#include "kernels_a.cuh"
+namespace mmdb {
+MMDB_INSTANTIATE_CLASS(0, 0, 3, 1)
+MMDB_INSTANTIATE_CLASS(1, 0, 3, 1)
+MMDB_INSTANTIATE_CLASS(3, 1, 3, 0)
+}

@@ -11,6 +11,10 @@ namespace mmdb {
 
 constexpr int KA_THREADS = 128;
 
+// LA..LD are shell TYPE codes (core.cuh: 3 = S2, a two-component s pseudo-shell); ltot = total angular momentum
+__host__ __device__ constexpr int ltot(int la, int lb, int lc, int ld) { return am_of(la) + am_of(lb) + am_of(lc) + am_of(ld); }
+__host__ __device__ constexpr bool has_s2(int la, int lb, int lc, int ld) { return la == SH_S2 || lb == SH_S2 || lc == SH_S2 || ld == SH_S2; }
+
 __host__ __device__ constexpr int etab_size(int la, int lb)
 {
     int n = 0;
@@ -26,31 +30,33 @@ __host__ __device__ constexpr bool scratch_out()
 {
     // (dp|ps) (three ket component pairs in all) stays with one pair per thread and three CTAs per quartet: measured
     // 6.5 ms against 6.9 ms with the scratch column; (dp|pp) went from 6.3 to 5.0 ms, (dp|ds) from 3.3 to 3.1 ms
-    return LA == 2 && LB == 1 && ncart(LC) * ncart(LD) >= 6;
+    return LA == 2 && LB == 1 && ncomp(LC) * ncomp(LD) >= 6;
 }
 
 // R_tuv lives in shared memory (one column per thread) for the high-L classes, in registers otherwise
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr bool r_in_smem()
 {
-    return LA + LB + LC + LD >= 5 || scratch_out<LA, LB, LC, LD>();
+    return ltot(LA, LB, LC, LD) >= 5 || scratch_out<LA, LB, LC, LD>();
 }
 
 // ket component pairs per chunk
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr int chunk_ncd()
 {
-    constexpr int NAB = ncart(LA) * ncart(LB), NCD = ncart(LC) * ncart(LD), NHB = nherm(LA + LB);
+    constexpr int NAB = ncomp(LA) * ncomp(LB), NCD = ncomp(LC) * ncomp(LD), NHB = nherm(am_of(LA) + am_of(LB));
     int best = 1;
     if (scratch_out<LA, LB, LC, LD>()) return 3;
     if (r_in_smem<LA, LB, LC, LD>()) {
         // live doubles: ket transform G + ket E table; bra transform G + out + bra E table
-        constexpr int nEb = 3 * etab_size(LA, LB), nEk = 3 * etab_size(LC, LD);
+        constexpr int nEb = 3 * etab_size(am_of(LA), am_of(LB)), nEk = 3 * etab_size(am_of(LC), am_of(LD));
         for (int c = 1; c <= NCD; ++c)
             if (NCD % c == 0 && NHB * c + nEk <= 112 && (NAB + NHB) * c + nEb <= 124) best = c;
     } else {
+        // (classes with an S2 pseudo-shell and L >= 3: smaller chunks, their digestion blocks are wider)
+        constexpr int out_max = (has_s2(LA, LB, LC, LD) && ltot(LA, LB, LC, LD) >= 3) ? 24 : 36;
         for (int c = 1; c <= NCD; ++c)
-            if (NCD % c == 0 && NAB * c <= 36 && NHB * c <= 40) best = c;
+            if (NCD % c == 0 && NAB * c <= out_max && NHB * c <= 40) best = c;
     }
     return best;
 }
@@ -59,7 +65,7 @@ __host__ __device__ constexpr int chunk_ncd()
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr bool block_chunks()
 {
-    return ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() >= 2;
+    return ncomp(LC) * ncomp(LD) / chunk_ncd<LA, LB, LC, LD>() >= 2;
 }
 
 // CTA shape.  The L <= 2 classes run ONE large CTA per SM (as many warps as their register use allows:
@@ -70,10 +76,18 @@ __host__ __device__ constexpr bool block_chunks()
 template <int LA, int LB, int LC, int LD, bool FAR = false>
 __host__ __device__ constexpr int ka_threads()
 {
-    constexpr int L = LA + LB + LC + LD;
+    constexpr int L = ltot(LA, LB, LC, LD);
     // far-list kernels stage no Boys table, so nothing is gained by one huge CTA per SM: 256-thread CTAs, as many
     // as the register budget of min_blocks allows
     if (FAR && L <= 2) return 256;
+    if (has_s2(LA, LB, LC, LD) && L <= 2) {
+        // classes with an S2 pseudo-shell: the blocks are larger than those of the plain class of the same L
+        // (thread count = register cap; chosen from the ptxas logs so that none of these spills)
+        constexpr int NFN = ncomp(LA) * ncomp(LB) * ncomp(LC) * ncomp(LD);
+        if (L == 0) return NFN <= 2 ? 640 : (NFN == 4 ? (LC == SH_S2 ? 512 : 640) : (NFN == 8 ? 384 : 256));
+        if (L == 1) return NFN <= 6 ? 512 : (NFN <= 12 ? 384 : 256);
+        return 256;
+    }
     if (L == 0) return 768;                      // 80 registers
     if (L == 1) return 640;                      // 96 registers (768 threads at 80 registers: slower)
     if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
@@ -89,7 +103,7 @@ __host__ __device__ constexpr int ka_threads()
 template <int LA, int LB, int LC, int LD, bool FAR = false>
 __host__ __device__ constexpr int min_blocks()
 {
-    constexpr int L = LA + LB + LC + LD;
+    constexpr int L = ltot(LA, LB, LC, LD);
     if (FAR && L == 0) return 4;                 // <= 64 registers
     if (FAR && L == 1) return 3;                 // <= 80 registers
     if (FAR && L == 2) return (LA == 2) ? 2 : 1; // (ds|ss) <= 128 registers; (ps|ps), (pp|ss) as the register use falls
@@ -102,8 +116,8 @@ __host__ __device__ constexpr int min_blocks()
 template <int LA, int LB, int LC, int LD, bool FAR = false>
 __host__ __device__ constexpr size_t class_smem_bytes()
 {
-    size_t b = FAR ? 0 : (size_t)boys_rows(LA + LB + LC + LD) * BOYS_STRIDE * sizeof(double);
-    if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(LA + LB + LC + LD) * ka_threads<LA, LB, LC, LD, FAR>() * sizeof(double);
+    size_t b = FAR ? 0 : (size_t)boys_rows(ltot(LA, LB, LC, LD)) * BOYS_STRIDE * sizeof(double);
+    if (r_in_smem<LA, LB, LC, LD>()) b += (size_t)nherm(ltot(LA, LB, LC, LD)) * ka_threads<LA, LB, LC, LD, FAR>() * sizeof(double);
     return b;
 }
 
@@ -164,9 +178,9 @@ __device__ __forceinline__ DigestGeom make_geom(int N, int bfA, int bfB, int bfC
 
 template <int LA, int LB, int LC, int LD, int CD0, int NCDC>
 __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestGeom &g, bool active, bool ket_uniform,
-                                             const double (&out)[ncart(LA) * ncart(LB) * NCDC])
+                                             const double (&out)[ncomp(LA) * ncomp(LB) * NCDC])
 {
-    constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+    constexpr int NA = ncomp(LA), NB = ncomp(LB), NC = ncomp(LC), ND = ncomp(LD);
     // which c / d components this chunk touches
     auto need_c = [](int c) constexpr { for (int x = CD0; x < CD0 + NCDC; ++x) if (x / ND == c) return true; return false; };
     auto need_d = [](int d) constexpr { for (int x = CD0; x < CD0 + NCDC; ++x) if (x % ND == d) return true; return false; };
@@ -211,7 +225,7 @@ __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestG
             sfor<0, NB>([&](auto B_) {
                 constexpr int b = decltype(B_)::value;
                 constexpr int ab = a * NB + b;
-                constexpr double sab = comp_scale(LA, a) * comp_scale(LB, b);
+                constexpr double sab = cscale(LA, a) * cscale(LB, b);
                 const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
                 const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
                 const double pab4 = 4.0 * fabs(pab);
@@ -222,7 +236,7 @@ __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestG
                     constexpr int cdi = decltype(J)::value;
                     constexpr int cd = CD0 + cdi;
                     constexpr int c = cd / ND, d = cd % ND;
-                    constexpr double s8 = 8.0 * sab * comp_scale(LC, c) * comp_scale(LD, d);
+                    constexpr double s8 = 8.0 * sab * cscale(LC, c) * cscale(LD, d);
                     double w = wab;
                     if constexpr (LC == LD) w *= g.sameCD ? (c > d ? 1.0 : (c == d ? 0.5 : 0.0)) : 1.0;
                     double dmax = fmax(pab4, 4.0 * fabs(Pcd[cdi]));
@@ -293,7 +307,7 @@ template <int LA, int LB, int LC, int LD>
 __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB, int bfC, int bfD, int c, int d, double scd,
                                           bool active, bool ket_uniform, const double *__restrict__ out, long long ostride)
 {
-    constexpr int NA = ncart(LA), NB = ncart(LB);
+    constexpr int NA = ncomp(LA), NB = ncomp(LB);
     const DigestGeom g = make_geom(dg.N, bfA, bfB, bfC, bfD);
     const double *__restrict__ P = dg.dPre;
     const double *__restrict__ SQ = dg.SQ;
@@ -331,7 +345,7 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
             const double ma = fmax(pcd4, fmax(fabs(pac), fabs(pad)));                // shared by every b
             sfor<0, NB>([&](auto B_) {
                 constexpr int b = decltype(B_)::value;
-                constexpr double s8 = 8.0 * comp_scale(LA, a) * comp_scale(LB, b);
+                constexpr double s8 = 8.0 * cscale(LA, a) * cscale(LB, b);
                 const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
                 const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
                 double wab = 1.0;
@@ -369,7 +383,7 @@ template <bool FIXED>
 static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, const PairHdr &bh, const PairHdr &kh, bool samePair,
                                                int la, int lb, int lc, int ld, int cd0, int ncdc, const double *vals)
 {
-    const int nb = ncart(lb), nd = ncart(ld), nab = ncart(la) * nb;
+    const int nb = ncomp(lb), nd = ncomp(ld), nab = ncomp(la) * nb;
     const bool sameAB = (bh.shA == bh.shB), sameCD = (kh.shA == kh.shB);
     for (int ab = 0; ab < nab; ++ab) {
         const int aa = ab / nb, bb = ab % nb;
@@ -390,7 +404,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
                                           const PairHdr &kh, const double *boys_tab, bool samePair, bool ket_uniform,
                                           int ib0, int ib1)
 {
-    constexpr int NA = ncart(LA), NB = ncart(LB), NC = ncart(LC), ND = ncart(LD);
+    constexpr int NA = ncomp(LA), NB = ncomp(LB), NC = ncomp(LC), ND = ncomp(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND;
     double out[NAB * NCDC];
     constexpr bool SCR = scratch_out<LA, LB, LC, LD>();
@@ -399,8 +413,8 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     double *scr = SCR ? a.scratch + ((long long)blockIdx.x * blockDim.x + threadIdx.x) : nullptr;
     if (valid)
         eval_quartet_chunk<LA, LB, LC, LD, CD0, NCDC, r_in_smem<LA, LB, LC, LD>(), SERIAL_CHUNKS, FAR, SCR>(
-            bh, BraSrc{a.braS, a.braRow, a.braN, ibra}, kh, a.ketP, boys_tab,
-            const_cast<double *>(boys_tab) + (FAR ? 0 : boys_rows(LA + LB + LC + LD) * BOYS_STRIDE) + threadIdx.x,
+            bh, BraSrc{a.braS, a.braRow, a.braN, ibra, a.braW}, kh, a.ketP, a.ketW, boys_tab,
+            const_cast<double *>(boys_tab) + (FAR ? 0 : boys_rows(ltot(LA, LB, LC, LD)) * BOYS_STRIDE) + threadIdx.x,
             ka_threads<LA, LB, LC, LD, FAR>(), ib0, ib1, out, scr, sstride);
     if constexpr (SCR) {
         if constexpr (EPI == EPI_STORE) {
@@ -408,11 +422,11 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
                 double *o = a.out + e * (unsigned long long)(NAB * NCD);
                 sfor<0, NAB>([&](auto ABI) {
                     constexpr int ab = decltype(ABI)::value;
-                    constexpr double sab = comp_scale(LA, ab / NB) * comp_scale(LB, ab % NB);
+                    constexpr double sab = cscale(LA, ab / NB) * cscale(LB, ab % NB);
                     sfor<0, NCDC>([&](auto CDI) {
                         constexpr int cdi = decltype(CDI)::value;
                         constexpr int cd = CD0 + cdi;
-                        constexpr double sc = sab * comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND);
+                        constexpr double sc = sab * cscale(LC, cd / ND) * cscale(LD, cd % ND);
                         o[ab * NCD + cd] = __ldcg(scr + (long long)(ab * NCDC + cdi) * sstride) * sc;
                     });
                 });
@@ -422,7 +436,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
                 constexpr int cdi = decltype(CDI)::value;
                 constexpr int cd = CD0 + cdi;
                 digest_cd_rt<LA, LB, LC, LD>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, cd / ND, cd % ND,
-                                             comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND), valid, ket_uniform,
+                                             cscale(LC, cd / ND) * cscale(LD, cd % ND), valid, ket_uniform,
                                              scr + (long long)cdi * sstride, (long long)NCDC * sstride);
             });
         } else {
@@ -441,11 +455,11 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
             double *o = a.out + e * (unsigned long long)(NAB * NCD);
             sfor<0, NAB>([&](auto ABI) {
                 constexpr int ab = decltype(ABI)::value;
-                constexpr double sab = comp_scale(LA, ab / NB) * comp_scale(LB, ab % NB);
+                constexpr double sab = cscale(LA, ab / NB) * cscale(LB, ab % NB);
                 sfor<0, NCDC>([&](auto CDI) {
                     constexpr int cdi = decltype(CDI)::value;
                     constexpr int cd = CD0 + cdi;
-                    constexpr double s = sab * comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND);
+                    constexpr double s = sab * cscale(LC, cd / ND) * cscale(LD, cd % ND);
                     o[ab * NCD + cd] = out[ab * NCDC + cdi] * s;
                 });
             });
@@ -461,7 +475,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
 #pragma unroll
                 for (int x = 0; x < NAB; ++x) tmp[x] = out[x * NCDC + cdi];
                 digest_cd_rt<LA, LB, LC, LD>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, cd / ND, cd % ND,
-                                             comp_scale(LC, cd / ND) * comp_scale(LD, cd % ND), valid, ket_uniform, tmp, 1);
+                                             cscale(LC, cd / ND) * cscale(LD, cd % ND), valid, ket_uniform, tmp, 1);
             });
         } else {
             const DigestGeom geom = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
@@ -485,7 +499,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
 template <int LA, int LB, int LC, int LD, int EPI, bool FAR = false>
 __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD, FAR>(), min_blocks<LA, LB, LC, LD, FAR>()) eri_class_kernel(const EriArgs a)
 {
-    constexpr int NCD = ncart(LC) * ncart(LD);
+    constexpr int NCD = ncomp(LC) * ncomp(LD);
     constexpr int NCDC = chunk_ncd<LA, LB, LC, LD>();
     constexpr int NCHUNK = NCD / NCDC;
     extern __shared__ double s_boys[];
@@ -496,13 +510,13 @@ __global__ void __launch_bounds__(ka_threads<LA, LB, LC, LD, FAR>(), min_blocks<
         if (first >= n) return;
     }
     if constexpr (!FAR) {
-        for (int x = threadIdx.x; x < boys_rows(LA + LB + LC + LD) * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
+        for (int x = threadIdx.x; x < boys_rows(ltot(LA, LB, LC, LD)) * BOYS_STRIDE; x += blockDim.x) s_boys[x] = __ldg(a.boys_tab + x);
         __syncthreads();
     }
     // Block-uniform trip count: every warp stays in the loop (the digestion uses warp shuffles) and, for the
     // classes whose unrolled code exceeds the instruction cache, the warps of a CTA are kept in step with a
     // barrier per quartet so they stream through the code together (one fetch serves all of them).
-    constexpr bool LOCKSTEP = (LA + LB + LC + LD >= 4);
+    constexpr bool LOCKSTEP = (ltot(LA, LB, LC, LD) >= 4);
     // Chunked classes: the ket-component chunk is a property of the CTA (blockIdx.x % NCHUNK), not a serial
     // loop inside the thread.  Each CTA then executes the code of ONE chunk for many quartets, so its
     // instruction working set is 1/NCHUNK of the kernel and stays cache-resident (ncu: stall_no_instruction
@@ -588,20 +602,23 @@ cudaError_t launch_class_impl(const EriArgs &a, int kind, int grid, cudaStream_t
     static int occ[LK_COUNT] = {0, 0, 0, 0};
     // far-field variants exist for L <= FAR_MAXL only: above that Boys + R are a small part of a primitive quartet and the
     // extra launch per class pair costs more than the table branch it saves (lib.cu sends everything to the near list)
-    constexpr bool HAS_FAR = (LA + LB + LC + LD <= FAR_MAXL);
-    if (occ[0] == 0) {
-        setup_kernel<LA, LB, LC, LD, EPI_STORE, false>(&occ[LK_STORE]);
+    constexpr bool HAS_FAR = (ltot(LA, LB, LC, LD) <= FAR_MAXL) && !has_s2(LA, LB, LC, LD);
+    // classes with an S2 pseudo-shell exist for the direct Fock build only: no integral-storing variant
+    constexpr bool HAS_STORE = !has_s2(LA, LB, LC, LD);
+    if (occ[LK_DIGEST] == 0) {
+        if constexpr (HAS_STORE) setup_kernel<LA, LB, LC, LD, EPI_STORE, false>(&occ[LK_STORE]);
         setup_kernel<LA, LB, LC, LD, EPI_DIGEST, false>(&occ[LK_DIGEST]);
         setup_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW, false>(&occ[LK_DIGEST_SLOW]);
         if constexpr (HAS_FAR) setup_kernel<LA, LB, LC, LD, EPI_DIGEST, true>(&occ[LK_DIGEST_FAR]);
     }
-    constexpr int NCH = block_chunks<LA, LB, LC, LD>() ? ncart(LC) * ncart(LD) / chunk_ncd<LA, LB, LC, LD>() : 1;
+    constexpr int NCH = block_chunks<LA, LB, LC, LD>() ? ncomp(LC) * ncomp(LD) / chunk_ncd<LA, LB, LC, LD>() : 1;
     auto shape = [&](int o) { return std::max(NCH, (grid * o) / NCH * NCH); };   // multiple of the chunk count
     constexpr int threads = ka_threads<LA, LB, LC, LD, false>();
     constexpr size_t smem = class_smem_bytes<LA, LB, LC, LD, false>();
-    if (kind == LK_STORE)
-        eri_class_kernel<LA, LB, LC, LD, EPI_STORE, false><<<shape(occ[kind]), threads, smem, st>>>(a);
-    else if (kind == LK_DIGEST)
+    if (kind == LK_STORE) {
+        if constexpr (HAS_STORE) eri_class_kernel<LA, LB, LC, LD, EPI_STORE, false><<<shape(occ[kind]), threads, smem, st>>>(a);
+        else return cudaErrorInvalidValue;
+    } else if (kind == LK_DIGEST)
         eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST, false><<<shape(occ[kind]), threads, smem, st>>>(a);
     else if (kind == LK_DIGEST_SLOW)
         eri_class_kernel<LA, LB, LC, LD, EPI_DIGEST_SLOW, false><<<shape(occ[kind]), threads, smem, st>>>(a);

@@ -129,10 +129,14 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
 {
     if (!b) return MMDB_OK;
     cudaSetDevice(b->device);
-    for (auto &p : b->pc) {
+    auto free_class = [](PairClass &p) {
         cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.prim_ab_dev); cudaFree(p.prim_soa_dev); cudaFree(p.prim_row_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
         cudaFree(p.sbase_dev); cudaFree(p.sgeo_dev); cudaFree(p.spmin_dev); cudaFree(p.geo_dev); cudaFree(p.pmin_dev);
-    }
+        cudaFree(p.Kref_dev); cudaFree(p.wgt_dev); cudaFree(p.wgt_soa_dev);
+    };
+    for (auto &p : b->pc) free_class(p);
+    for (auto &p : b->pcg) free_class(p);
+    cudaFree(b->shg_bf0_dev); cudaFree(b->shg_nf_dev); cudaFree(b->DSg_dev);
     for (auto &t : b->boys_dev) cudaFree(t);
     cudaFree(b->sh_bf0_dev); cudaFree(b->sh_nf_dev); cudaFree(b->Q_dev); cudaFree(b->SQ_dev);
     cudaFree(b->Dabs_dev); cudaFree(b->DS_dev); cudaFree(b->dglob_dev); cudaFree(b->list_dev);
@@ -195,66 +199,85 @@ extern "C" int mmdb_basis_create(int device, int nshell, const int *am, const in
     return MMDB_OK;
 }
 
-static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *am, const int *nprim, const int *prim_off,
-                             const double *centre, const double *exps, const double *coefs, const int *bf0, double prim_cut)
+// pair classes by shell TYPE codes: the six plain ones (index la(la+1)/2 + lb) and, for the grouped shell list of the
+// direct Fock build, (S2 s), (S2 p), (S2 S2)
+static const int GC_CLASS[MMDB_NCLASS_GC][2] = {{0, 0}, {1, 0}, {1, 1}, {2, 0}, {2, 1}, {2, 2}, {3, 0}, {3, 1}, {3, 3}};
+static int gc_class_index(int ta, int tb)
 {
-    b->nshell = nshell;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    b->nsm = prop.multiProcessorCount;
-    int ntot = 0, nbf = 0;
-    for (int s = 0; s < nshell; ++s) {
-        if (am[s] < 0 || am[s] > MMDB_MAX_AM) {
-            return fail(MMDB_ERR_UNSUPPORTED, "mmdb_basis_create: angular momentum > d is not supported on the device path");
-        }
-        ShellH h{am[s], nprim[s], prim_off[s], bf0[s], centre[3 * s], centre[3 * s + 1], centre[3 * s + 2]};
-        b->sh.push_back(h);
-        ntot = std::max(ntot, prim_off[s] + nprim[s]);
-        nbf = std::max(nbf, bf0[s] + ncart(am[s]));
-    }
-    b->nbf = nbf;
-    b->exps.assign(exps, exps + ntot);
-    b->coefs.assign(coefs, coefs + ntot);
+    for (int c = 0; c < MMDB_NCLASS_GC; ++c)
+        if (GC_CLASS[c][0] == ta && GC_CLASS[c][1] == tb) return c;
+    return -1;
+}
 
-    // ---- shell pairs, by class; am[A] >= am[B], equal am: A >= B --------------------------------
+// Shell pairs of one shell list, class by class, with every device table the kernels and the screen read.
+static int build_pairs(mmdb_basis *b, const std::vector<ShellH> &sh, PairClass *pcs, int nclass, bool gc, double prim_cut)
+{
+    // type[A] >= type[B], equal types: A >= B
+    const int nshell = (int)sh.size();
     const double SQRT2_PI54 = std::sqrt(2.0) * std::pow(M_PI, 1.25);
-    for (int la = 0; la <= MMDB_MAX_AM; ++la)
-        for (int lb = 0; lb <= la; ++lb) {
-            PairClass &P = b->pc[pc_index(la, lb)];
-            P.la = la;
-            P.lb = lb;
-        }
+    for (int c = 0; c < nclass; ++c) {
+        pcs[c].la = GC_CLASS[c][0];
+        pcs[c].lb = GC_CLASS[c][1];
+    }
     struct Tmp {
         PairHdr h;
         std::vector<PrimPair> pp;
         std::vector<double2> ab;       // (exponent on A, exponent on B) of every primitive pair, same order as pp
+        std::vector<double> w;         // MAX_WGT contraction weights per primitive pair (pairs with an S2 member)
+        int kref = 0;                  // primitive pairs summed over the member contractions (each with its own cut)
     };
-    std::vector<Tmp> tmp[MMDB_NCLASS_PAIR];
+    std::vector<Tmp> tmp[MMDB_NCLASS_GC];
+    // (S2, d) pairs are expanded into the two plain (d, s) pairs of the members: the d classes keep their kernels
+    std::vector<std::pair<ShellH, ShellH>> todo;
     for (int A = 0; A < nshell; ++A)
         for (int B = 0; B <= A; ++B) {
             int a = A, c = B;
-            if (b->sh[a].am < b->sh[c].am) std::swap(a, c);
-            const ShellH &sa = b->sh[a], &sb = b->sh[c];
+            if (sh[a].am < sh[c].am) std::swap(a, c);
+            if (sh[a].am == SH_S2 && sh[c].am == 2) {
+                for (int m = 0; m < 2; ++m) {
+                    ShellH mem = sh[a];
+                    mem.am = 0;
+                    if (m) mem.poff = mem.poff2;      // coefficients of the second contraction (exponents are equal)
+                    mem.bf0 += m;
+                    todo.push_back({sh[c], mem});
+                }
+            } else {
+                todo.push_back({sh[a], sh[c]});
+            }
+        }
+    for (const auto &pr : todo) {
+        {
+            const ShellH &sa = pr.first, &sb = pr.second;
             const double ABx = sa.x - sb.x, ABy = sa.y - sb.y, ABz = sa.z - sb.z;
             const double AB2 = ABx * ABx + ABy * ABy + ABz * ABz;
             Tmp t;
             std::memset(&t.h, 0, sizeof(PairHdr));
-            t.h.bfA = sa.bf0; t.h.bfB = sb.bf0; t.h.shA = a; t.h.shB = c;
+            t.h.bfA = sa.bf0; t.h.bfB = sb.bf0; t.h.shA = sa.id; t.h.shB = sb.id;
             t.h.ABx = ABx; t.h.ABy = ABy; t.h.ABz = ABz; t.h.Qs = 0.0;
-            const int lab = sa.am + sb.am;
+            const int lab = am_of(sa.am) + am_of(sb.am);
+            const int nwa = sa.am == SH_S2 ? 2 : 1, nwb = sb.am == SH_S2 ? 2 : 1, nw = nwa * nwb;
             for (int i = 0; i < sa.nprim; ++i)
                 for (int j = 0; j < sb.nprim; ++j) {
                     const double ea = b->exps[sa.poff + i], eb = b->exps[sb.poff + j];
                     const double p = ea + eb, mu = ea * eb / p;
                     const double K = std::exp(-mu * AB2);
-                    const double c2 = b->coefs[sa.poff + i] * b->coefs[sb.poff + j];
-                    if (prim_cut > 0) {
+                    // contraction weights per member pair; a plain pair has one and folds it into cc
+                    double w[MAX_WGT] = {0.0, 0.0, 0.0, 0.0};
+                    for (int ma = 0; ma < nwa; ++ma)
+                        for (int mb = 0; mb < nwb; ++mb)
+                            w[ma * nwb + mb] = b->coefs[(ma ? sa.poff2 : sa.poff) + i] * b->coefs[(mb ? sb.poff2 : sb.poff) + j];
+                    const double c2 = (nw == 1) ? w[0] : 1.0;
+                    int nkeep = 0;
+                    for (int m = 0; m < nw; ++m) {
                         // magnitude estimate: sqrt of the primitive (ss|ss)-like self repulsion, with a
                         // generous polynomial allowance for the angular factors
-                        double est = std::fabs(c2) * K * std::pow(M_PI, 1.25) * std::pow(2.0, 0.25) / std::pow(p, 1.25);
+                        double est = std::fabs(w[m]) * K * std::pow(M_PI, 1.25) * std::pow(2.0, 0.25) / std::pow(p, 1.25);
                         est *= std::pow(1.0 + std::sqrt(AB2), lab) * std::pow(std::max(1.0, p), 0.5 * lab) * 16.0;
-                        if (est < prim_cut) continue;
+                        if (prim_cut > 0 && est < prim_cut) w[m] = 0.0;      // this member drops the primitive, as its plain pair would
+                        else ++nkeep;
                     }
+                    if (nkeep == 0) continue;
+                    t.kref += nkeep;
                     PrimPair q;
                     q.p = p;
                     q.Px = (ea * sa.x + eb * sb.x) / p;
@@ -266,6 +289,7 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
                     q.cc = c2 * K * SQRT2_PI54 / (p * std::sqrt(p)) * std::sqrt(SQRTPI_2);
                     t.pp.push_back(q);
                     t.ab.push_back(make_double2(ea, eb));
+                    t.w.insert(t.w.end(), w, w + MAX_WGT);
                 }
             if (t.pp.empty()) continue;
             // tight primitive pairs first: the slices of a virtual bra pair then hold primitives of similar exponent, and
@@ -276,16 +300,25 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
                 std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return t.pp[x].p > t.pp[y].p; });
                 std::vector<PrimPair> pp2(ord.size());
                 std::vector<double2> ab2(ord.size());
-                for (size_t x = 0; x < ord.size(); ++x) { pp2[x] = t.pp[ord[x]]; ab2[x] = t.ab[ord[x]]; }
+                std::vector<double> w2(t.w.size());
+                for (size_t x = 0; x < ord.size(); ++x) {
+                    pp2[x] = t.pp[ord[x]]; ab2[x] = t.ab[ord[x]];
+                    for (int m = 0; m < MAX_WGT; ++m) w2[x * MAX_WGT + m] = t.w[(size_t)ord[x] * MAX_WGT + m];
+                }
                 t.pp.swap(pp2);
                 t.ab.swap(ab2);
+                t.w.swap(w2);
             }
             t.h.pnum = (int)t.pp.size();
-            tmp[pc_index(sa.am, sb.am)].push_back(std::move(t));
+            const int cls = gc_class_index(sa.am, sb.am);
+            if (cls < 0 || cls >= nclass) return fail(MMDB_ERR_INVALID, "build_pairs: pair class out of range");
+            tmp[cls].push_back(std::move(t));
         }
-    for (int c = 0; c < MMDB_NCLASS_PAIR; ++c) {
-        PairClass &P = b->pc[c];
+    }
+    for (int c = 0; c < nclass; ++c) {
+        PairClass &P = pcs[c];
         auto &v = tmp[c];
+        const bool weighted = nwgt(P.la, P.lb) > 1;
         // homogeneous contraction depth inside a warp: order by primitive-pair count (desc); inside one depth by an ESTIMATE
         // of the Schwarz bound (desc), so the pairs that can survive a weak ket row are a prefix of every depth group and
         // the screening kernel drops the rest tile by tile on its chunk maxima (which use the exact bounds).  The estimate:
@@ -293,8 +326,15 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         const bool sort_q = getenv("MMDB_PAIR_SORT") ? atoi(getenv("MMDB_PAIR_SORT")) != 0 : true;
         for (auto &t : v) {
             double q = 0.0;
-            for (const PrimPair &x : t.pp)
-                for (const PrimPair &y : t.pp) q += std::fabs(x.cc * y.cc) * std::sqrt(x.p * y.p / (x.p + y.p));
+            std::vector<double> wm(t.pp.size(), 1.0);       // largest member weight of every primitive pair
+            if (weighted)
+                for (size_t x = 0; x < t.pp.size(); ++x) {
+                    wm[x] = 0.0;
+                    for (int m = 0; m < MAX_WGT; ++m) wm[x] = std::max(wm[x], std::fabs(t.w[x * MAX_WGT + m]));
+                }
+            for (size_t x = 0; x < t.pp.size(); ++x)
+                for (size_t y = 0; y < t.pp.size(); ++y)
+                    q += std::fabs(t.pp[x].cc * wm[x] * t.pp[y].cc * wm[y]) * std::sqrt(t.pp[x].p * t.pp[y].p / (t.pp[x].p + t.pp[y].p));
             t.h.Qs = sort_q ? std::sqrt(q) : 0.0;      // overwritten with the exact bound by mmdb_schwarz
         }
         std::stable_sort(v.begin(), v.end(), [](const Tmp &x, const Tmp &y) {
@@ -305,11 +345,15 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         });
         P.npairs = (int)v.size();
         std::vector<double2> prim_ab;
+        std::vector<double> wgt;
+        std::vector<int> Kref;
         for (auto &t : v) {
             t.h.poff = (int)P.prim.size();
             t.h.pad0 = (int)P.hdr.size();        // own index in the class (virtual pairs carry their parent's here)
             P.prim.insert(P.prim.end(), t.pp.begin(), t.pp.end());
             prim_ab.insert(prim_ab.end(), t.ab.begin(), t.ab.end());
+            if (weighted) wgt.insert(wgt.end(), t.w.begin(), t.w.end());
+            Kref.push_back(t.kref | (nwgt(P.la, P.lb) << 24));
             P.hdr.push_back(t.h);
         }
         P.nprimpairs = (int64_t)P.prim.size();
@@ -326,11 +370,19 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         CU(cudaMalloc(&P.Qs_dev, sizeof(double) * P.npairs));
         CU(cudaMalloc(&P.Qmax_dev, sizeof(double) * ((P.npairs + 255) / 256)));
         CU(cudaMalloc(&P.K_dev, sizeof(int) * P.npairs));
+        CU(cudaMalloc(&P.Kref_dev, sizeof(int) * P.npairs));
+        CU(cudaMemcpy(P.Kref_dev, Kref.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
+        if (weighted) {
+            CU(cudaMalloc(&P.wgt_dev, sizeof(double) * wgt.size()));
+            CU(cudaMemcpy(P.wgt_dev, wgt.data(), sizeof(double) * wgt.size(), cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&P.sh_dev, sizeof(int2) * P.npairs));
         CU(cudaMemcpy(P.hdr_dev, P.hdr.data(), sizeof(PairHdr) * P.npairs, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(P.prim_dev, P.prim.data(), sizeof(PrimPair) * P.prim.size(), cudaMemcpyHostToDevice));
-        CU(cudaMalloc(&P.prim_ab_dev, sizeof(double2) * prim_ab.size()));
-        CU(cudaMemcpy(P.prim_ab_dev, prim_ab.data(), sizeof(double2) * prim_ab.size(), cudaMemcpyHostToDevice));
+        if (!gc) {
+            CU(cudaMalloc(&P.prim_ab_dev, sizeof(double2) * prim_ab.size()));
+            CU(cudaMemcpy(P.prim_ab_dev, prim_ab.data(), sizeof(double2) * prim_ab.size(), cudaMemcpyHostToDevice));
+        }
         {   // structure-of-arrays copy for the bra side (see BraSrc in core.cuh); pairs are sorted by pnum (desc),
             // so primitive k exists for the first n_k pairs and row k holds exactly those
             const int kmax = P.hdr[0].pnum;
@@ -348,6 +400,14 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
                     const double f[8] = {q.Px, q.Py, q.Pz, q.p, q.cc, q.PAx, q.PAy, q.PAz};
                     for (int x = 0; x < 8; ++x) soa[(size_t)x * nprim + row[k] + i] = f[x];
                 }
+            if (weighted) {
+                std::vector<double> wsoa((size_t)MAX_WGT * nprim);
+                for (int i = 0; i < P.npairs; ++i)
+                    for (int k = 0; k < P.hdr[i].pnum; ++k)
+                        for (int x = 0; x < MAX_WGT; ++x) wsoa[(size_t)x * nprim + row[k] + i] = wgt[(size_t)(P.hdr[i].poff + k) * MAX_WGT + x];
+                CU(cudaMalloc(&P.wgt_soa_dev, sizeof(double) * wsoa.size()));
+                CU(cudaMemcpy(P.wgt_soa_dev, wsoa.data(), sizeof(double) * wsoa.size(), cudaMemcpyHostToDevice));
+            }
             CU(cudaMalloc(&P.prim_soa_dev, sizeof(double) * soa.size()));
             CU(cudaMalloc(&P.prim_row_dev, sizeof(long long) * kmax));
             CU(cudaMemcpy(P.prim_soa_dev, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice));
@@ -386,6 +446,93 @@ static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *a
         CU(cudaMemset(P.Qs_dev, 0, sizeof(double) * P.npairs));
         CU(cudaMemcpy(P.K_dev, K.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(P.sh_dev, shs.data(), sizeof(int2) * P.npairs, cudaMemcpyHostToDevice));
+    }
+    return MMDB_OK;
+}
+
+static int basis_create_impl(mmdb_basis *b, int device, int nshell, const int *am, const int *nprim, const int *prim_off,
+                             const double *centre, const double *exps, const double *coefs, const int *bf0, double prim_cut)
+{
+    b->nshell = nshell;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    b->nsm = prop.multiProcessorCount;
+    int ntot = 0, nbf = 0;
+    for (int s = 0; s < nshell; ++s) {
+        if (am[s] < 0 || am[s] > MMDB_MAX_AM) {
+            return fail(MMDB_ERR_UNSUPPORTED, "mmdb_basis_create: angular momentum > d is not supported on the device path");
+        }
+        ShellH h{am[s], nprim[s], prim_off[s], bf0[s], centre[3 * s], centre[3 * s + 1], centre[3 * s + 2]};
+        b->sh.push_back(h);
+        ntot = std::max(ntot, prim_off[s] + nprim[s]);
+        nbf = std::max(nbf, bf0[s] + ncart(am[s]));
+    }
+    b->nbf = nbf;
+    b->exps.assign(exps, exps + ntot);
+    b->coefs.assign(coefs, coefs + ntot);
+
+    // ---- shell pairs, by class --------------------------------------------------------------------
+    for (int s = 0; s < nshell; ++s) b->sh[s].id = s;
+    CHK(build_pairs(b, b->sh, b->pc, MMDB_NCLASS_PAIR, false, prim_cut));
+    // ---- grouped shell list of the direct Fock build: two consecutive s shells on one centre with identical exponents
+    // and adjacent functions (a generally contracted pair, e.g. the first two s functions of cc-pVDZ oxygen) become ONE
+    // S2 pseudo-shell whose primitive integrals are evaluated once
+    {
+        std::vector<char> used(nshell, 0);
+        for (int s = 0; s < nshell; ++s) {
+            if (used[s]) continue;
+            ShellH h = b->sh[s];
+            // MMDB_GC_MODE: 0 = no grouping, 1 (default) = s shells with identical primitives, 2 = any two consecutive s
+            // shells of one centre: the pseudo-shell then runs over the UNION of their primitives with zero coefficients
+            // where a member lacks one (shares the pair / quartet / digestion bookkeeping but saves no primitive; measured
+            // on (H2O)32/cc-pVDZ: screening 11 -> 7 ms, but the wide S2 kernels then carry everything: 73.8 -> 86.8 ms)
+            const int gc_mode = getenv("MMDB_NO_GC") ? 0 : (getenv("MMDB_GC_MODE") ? atoi(getenv("MMDB_GC_MODE")) : 1);
+            if (h.am == 0 && s + 1 < nshell && gc_mode > 0) {
+                const ShellH &g = b->sh[s + 1];
+                const bool partner = g.am == 0 && g.bf0 == h.bf0 + 1 && g.x == h.x && g.y == h.y && g.z == h.z;
+                bool same = partner && g.nprim == h.nprim;
+                for (int k = 0; same && k < h.nprim; ++k) same = b->exps[h.poff + k] == b->exps[g.poff + k];
+                if (same && h.nprim > 1) {
+                    h.am = SH_S2;
+                    h.poff2 = g.poff;
+                    used[s + 1] = 1;
+                    b->have_gc = true;
+                } else if (partner && gc_mode >= 2) {
+                    std::vector<double> U, cA, cB;
+                    for (int k = 0; k < h.nprim; ++k) { U.push_back(b->exps[h.poff + k]); cA.push_back(b->coefs[h.poff + k]); cB.push_back(0.0); }
+                    for (int k = 0; k < g.nprim; ++k) {
+                        size_t at = U.size();
+                        for (size_t x = 0; x < U.size(); ++x) if (U[x] == b->exps[g.poff + k]) at = x;
+                        if (at == U.size()) { U.push_back(b->exps[g.poff + k]); cA.push_back(0.0); cB.push_back(0.0); }
+                        cB[at] += b->coefs[g.poff + k];
+                    }
+                    // two parallel blocks (exponents, coefficients of member 0 / member 1) appended to the primitive arrays
+                    h.am = SH_S2;
+                    h.nprim = (int)U.size();
+                    h.poff = (int)b->exps.size();
+                    b->exps.insert(b->exps.end(), U.begin(), U.end());
+                    b->coefs.insert(b->coefs.end(), cA.begin(), cA.end());
+                    h.poff2 = (int)b->exps.size();
+                    b->exps.insert(b->exps.end(), U.begin(), U.end());
+                    b->coefs.insert(b->coefs.end(), cB.begin(), cB.end());
+                    used[s + 1] = 1;
+                    b->have_gc = true;
+                }
+            }
+            h.id = (int)b->shg.size();
+            b->shg.push_back(h);
+        }
+        b->nshellg = (int)b->shg.size();
+        if (b->have_gc) {
+            CHK(build_pairs(b, b->shg, b->pcg, MMDB_NCLASS_GC, true, prim_cut));
+            std::vector<int> f0(b->nshellg), nf(b->nshellg);
+            for (int s = 0; s < b->nshellg; ++s) { f0[s] = b->shg[s].bf0; nf[s] = ncomp(b->shg[s].am); }
+            CU(cudaMalloc(&b->shg_bf0_dev, sizeof(int) * b->nshellg));
+            CU(cudaMalloc(&b->shg_nf_dev, sizeof(int) * b->nshellg));
+            CU(cudaMemcpy(b->shg_bf0_dev, f0.data(), sizeof(int) * b->nshellg, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(b->shg_nf_dev, nf.data(), sizeof(int) * b->nshellg, cudaMemcpyHostToDevice));
+            CU(cudaMalloc(&b->DSg_dev, (size_t)b->nshellg * b->nshellg * sizeof(double)));
+        }
     }
     // ---- Boys tables --------------------------------------------------------------------------
     for (int L = 0; L <= BOYS_MAXL; ++L) {
@@ -450,26 +597,30 @@ DECL(2, 0, 0, 0) DECL(2, 0, 1, 0) DECL(2, 0, 1, 1) DECL(2, 0, 2, 0)
 DECL(2, 1, 0, 0) DECL(2, 1, 1, 0) DECL(2, 1, 1, 1) DECL(2, 1, 2, 0)
 DECL(2, 2, 0, 0) DECL(2, 2, 1, 0)
 DECL(2, 1, 2, 1) DECL(2, 2, 1, 1) DECL(2, 2, 2, 0) DECL(2, 2, 2, 1) DECL(2, 2, 2, 2)
+// classes with an S2 pseudo-shell (type code 3): direct Fock build only; ket = the more deeply contracted pair
+DECL(0, 0, 3, 0) DECL(1, 0, 3, 0) DECL(3, 0, 3, 0)
+DECL(0, 0, 3, 1) DECL(1, 0, 3, 1) DECL(3, 1, 3, 0) DECL(3, 1, 3, 1)
+DECL(0, 0, 3, 3) DECL(1, 0, 3, 3) DECL(3, 3, 3, 0) DECL(3, 3, 3, 1) DECL(3, 3, 3, 3)
 #undef DECL
 }  // namespace mmdb
 
 // every class (ss|ss) ... (dd|dd) has a class-specialised kernel; the generic runtime-L kernel (impl = 1) is the
 // independent cross-check
-// (la lb) >= (lc ld) in pair-class order is required
+// plain classes: (la lb) >= (lc ld) in pair-class order; classes with an S2 pseudo-shell: the instantiated orientations
 static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a, int kind, int impl, cudaStream_t st)
 {
-    const int L = la + lb + lc + ld;
+    const int L = am_of(la) + am_of(lb) + am_of(lc) + am_of(ld);      // la..ld are shell type codes
     a.boys_tab = b->boys_dev[L];
     CHK(ensure_eri_scratch(b));
     a.scratch = b->eri_scratch_dev + ((b->aux_stream != nullptr && st == b->aux_stream) ? eri_scratch_region(b)
                                        : ((b->main2_stream != nullptr && st == b->main2_stream) ? 2 * eri_scratch_region(b) : 0));
-    const int key = ((la * 3 + lb) * 3 + lc) * 3 + ld;
+    const int key = ((la * 4 + lb) * 4 + lc) * 4 + ld;
     cudaError_t e = cudaSuccess;
     const int gridA = b->nsm;   // x occupancy inside launch_class
     if (impl == 0) {
         switch (key) {
 #define CASE(LA, LB, LC, LD)                                  \
-    case ((LA * 3 + LB) * 3 + LC) * 3 + LD:                   \
+    case ((LA * 4 + LB) * 4 + LC) * 4 + LD:                   \
         e = launch_class<LA, LB, LC, LD>(a, kind, gridA, st); \
         break;
             CASE(0, 0, 0, 0) CASE(1, 0, 0, 0) CASE(1, 0, 1, 0) CASE(1, 1, 0, 0) CASE(1, 1, 1, 0) CASE(1, 1, 1, 1)
@@ -477,6 +628,9 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
             CASE(2, 1, 0, 0) CASE(2, 1, 1, 0) CASE(2, 1, 1, 1) CASE(2, 1, 2, 0)
             CASE(2, 2, 0, 0) CASE(2, 2, 1, 0)
             CASE(2, 1, 2, 1) CASE(2, 2, 1, 1) CASE(2, 2, 2, 0) CASE(2, 2, 2, 1) CASE(2, 2, 2, 2)
+            CASE(0, 0, 3, 0) CASE(1, 0, 3, 0) CASE(3, 0, 3, 0)
+            CASE(0, 0, 3, 1) CASE(1, 0, 3, 1) CASE(3, 1, 3, 0) CASE(3, 1, 3, 1)
+            CASE(0, 0, 3, 3) CASE(1, 0, 3, 3) CASE(3, 3, 3, 0) CASE(3, 3, 3, 1) CASE(3, 3, 3, 3)
 #undef CASE
             default:
                 return fail(MMDB_ERR_INVALID, "launch_eri: class not instantiated");
@@ -525,6 +679,19 @@ __global__ void schwarz_extract_kernel(const PairHdr *hdr, int npairs, int la, i
             SQ[(size_t)q * N + p] = s;
             qmax = fmax(qmax, sqrt(fabs(v)));
         }
+        Qs[i] = qmax;
+    }
+}
+
+// pair bounds of the grouped pair classes from the function-level table: Qs[i] = max over the pair's function pairs of sqrt|Q|
+__global__ void gc_bounds_kernel(const PairHdr *hdr, int npairs, int ta, int tb, int N, const double *Q, double *Qs)
+{
+    const int na = ncomp(ta), nb = ncomp(tb);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += gridDim.x * blockDim.x) {
+        const PairHdr h = hdr[i];
+        double qmax = 0.0;
+        for (int a = 0; a < na; ++a)
+            for (int c = 0; c < nb; ++c) qmax = fmax(qmax, sqrt(fabs(Q[(size_t)(h.bfA + a) * N + h.bfB + c])));
         Qs[i] = qmax;
     }
 }
@@ -578,6 +745,7 @@ struct ScreenArgs {
     const double *Qs_bra, *Qs_ket, *Qmax_bra;
     const int2 *sh_bra, *sh_ket;
     const int *K_bra, *K_ket;
+    const int *Kref_bra, *Kref_ket;        // statistics in units of the reference's shell quartets: primitive pairs | members << 24
     const int *sbase_bra;                  // first slice record of a bra pair
     const double4 *sgeo_bra, *geo_ket;     // bounding spheres of the product centres: per bra slice / per ket pair (or nullptr)
     const double *spmin_bra, *pmin_ket;    // smallest total exponent: per bra slice / per ket pair
@@ -594,7 +762,7 @@ struct ScreenArgs {
     uint2 *list_far, *list_near;
     unsigned long long *ctr;       // see CTR_* below
 };
-enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_PER_LAUNCH = 6 };
+enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_EXECPQ = 6, CTR_PER_LAUNCH = 7 };
 
 constexpr int SCR_THREADS = 256;
 #ifndef MMDB_SCR_CPT
@@ -608,6 +776,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
 {
     __shared__ unsigned long long s_wcnt[SCR_THREADS / 32];
     __shared__ unsigned long long s_wk[SCR_THREADS / 32];
+    __shared__ unsigned long long s_wx[SCR_THREADS / 32];
     __shared__ unsigned s_wcand[SCR_THREADS / 32];
     __shared__ unsigned long long s_base[3];
     __shared__ unsigned short s_slot[SCR_THREADS / 32][SCR_CPT * 32];    // compacted phase-1 survivors per warp
@@ -638,15 +807,18 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
             }
         }
         const int2 cd = s.sh_ket[j];
-        const unsigned long long kj = (unsigned long long)s.K_ket[j];
+        const unsigned krj = (unsigned)s.Kref_ket[j];
+        const unsigned long long kj = (unsigned long long)(krj & 0xffffffu);
+        const unsigned mj = krj >> 24;
+        const unsigned long long kxj = (unsigned long long)s.K_ket[j];
         // Two phases per warp (128 consecutive columns).  Phase 1: the cheap density-independent bound on all columns,
         // lane-strided (coalesced), survivors compacted into a per-warp slot array in column order.  Phase 2: the
         // six-block density test, slicing and list classification on the compacted survivors only.
         const int wbase = c0 + warp * (SCR_CPT * 32);
-        unsigned bits = 0, sbits = 0, ncand = 0;
+        unsigned bits = 0, sbits = 0, ncand = 0, nquart = 0;
         unsigned nsl[SCR_CPT], fmask[SCR_CPT];       // slices of the pair; which of them are far-field
         int col[SCR_CPT];
-        unsigned long long kk = 0;
+        unsigned long long kk = 0, kx = 0;      // primitive quartets: in the reference's units / actually evaluated
         const int hiK = s.split ? max(s.bf0[cd.x], s.bf0[cd.y]) : 0;
         double4 gk = make_double4(0.0, 0.0, 0.0, 0.0);
         double qmin = 0.0;
@@ -696,7 +868,10 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                 if (pass) {
                     bits |= 1u << k;
                     const int kb = s.K_bra[i];
-                    kk += (unsigned long long)kb * kj;
+                    const unsigned krb = (unsigned)s.Kref_bra[i];
+                    kk += (unsigned long long)(krb & 0xffffffu) * kj;
+                    nquart += (krb >> 24) * mj;
+                    kx += (unsigned long long)kb * kxj;
                     // one list entry per slice of BRA_SLICE bra primitive pairs (direct builds only)
                     nsl[k] = s.split ? (unsigned)((kb + BRA_SLICE - 1) / BRA_SLICE) : 1u;
                     bool slow = false;
@@ -734,24 +909,26 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
             const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        unsigned long long ks = kk;
-        unsigned cs = ncand | ((unsigned)__popc(bits) << 16);      // candidates | shell quartets (<= SCR_CPT each per thread)
+        unsigned long long ks = kk, xs = kx;
+        unsigned cs = ncand | (nquart << 16);      // candidates (<= SCR_CPT per thread) | shell quartets (<= 16 SCR_CPT per thread)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             ks += __shfl_xor_sync(0xffffffffu, ks, o);
+            xs += __shfl_xor_sync(0xffffffffu, xs, o);
             cs += __shfl_xor_sync(0xffffffffu, cs, o);
         }
         if (lane == 31) s_wcnt[warp] = incl;
-        if (lane == 0) { s_wk[warp] = ks; s_wcand[warp] = cs; }
+        if (lane == 0) { s_wk[warp] = ks; s_wx[warp] = xs; s_wcand[warp] = cs; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long tot = 0, tk = 0;
+            unsigned long long tot = 0, tk = 0, tx = 0;
             unsigned tc = 0, tq = 0;
             for (int w = 0; w < SCR_THREADS / 32; ++w) {
                 const unsigned long long c = s_wcnt[w];
                 s_wcnt[w] = tot;
                 tot += c;
                 tk += s_wk[w];
+                tx += s_wx[w];
                 tc += s_wcand[w] & 0xffffu;
                 tq += s_wcand[w] >> 16;
             }
@@ -761,6 +938,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
             s_base[1] = tn ? atomicAdd(s.ctr + CTR_NEAR, (unsigned long long)tn) : 0ull;
             s_base[2] = tsl ? atomicAdd(s.ctr + CTR_SLOW, (unsigned long long)tsl) : 0ull;
             if (tk) atomicAdd(s.ctr + CTR_PRIMQ, tk);
+            if (tx) atomicAdd(s.ctr + CTR_EXECPQ, tx);
             if (tc) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)tc);
         }
         __syncthreads();
@@ -848,6 +1026,20 @@ extern "C" int mmdb_eri_shell_quartets(mmdb_basis *b, int pc_bra, int pc_ket, in
     return launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_STORE, impl, st);
 }
 
+// the grouped pair classes take their bounds from the function-level table the plain classes have just filled
+static int gc_refresh_bounds(mmdb_basis *b, cudaStream_t st)
+{
+    if (!b->have_gc) return MMDB_OK;
+    for (int c = 0; c < MMDB_NCLASS_GC; ++c) {
+        PairClass &P = b->pcg[c];
+        if (P.npairs == 0) continue;
+        gc_bounds_kernel<<<(P.npairs + 127) / 128, 128, 0, st>>>(P.hdr_dev, P.npairs, P.la, P.lb, b->nbf, b->Q_dev, P.Qs_dev);
+        qs_chunk_max_kernel<<<((P.npairs + 255) / 256 + 3) / 4, 128, 0, st>>>(P.Qs_dev, P.npairs, P.Qmax_dev);
+    }
+    CU(cudaGetLastError());
+    return MMDB_OK;
+}
+
 extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
 {
     if (!b) return fail(MMDB_ERR_INVALID, "null handle");
@@ -873,6 +1065,7 @@ extern "C" int mmdb_schwarz(mmdb_basis *b, double *Q_dev, void *stream)
         qs_chunk_max_kernel<<<((P.npairs + 255) / 256 + 3) / 4, 128, 0, st>>>(P.Qs_dev, P.npairs, P.Qmax_dev);
     }
     CU(cudaGetLastError());
+    CHK(gc_refresh_bounds(b, st));
     if (Q_dev) CU(cudaMemcpyAsync(Q_dev, b->Q_dev, N2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     b->have_schwarz = true;
     return MMDB_OK;
@@ -890,24 +1083,25 @@ static bool far_enabled(int L)
 
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
                       bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, uint2 *list_far,
-                      uint2 *list_near, cudaStream_t st)
+                      uint2 *list_near, cudaStream_t st, bool gc = false)
 {
     ScreenArgs s;
     std::memset(&s, 0, sizeof(s));
     s.Qs_bra = B.Qs_dev; s.Qs_ket = K.Qs_dev; s.Qmax_bra = B.Qmax_dev; s.sh_bra = B.sh_dev; s.sh_ket = K.sh_dev;
-    s.K_bra = B.K_dev; s.K_ket = K.K_dev;
+    s.K_bra = B.K_dev; s.K_ket = K.K_dev; s.Kref_bra = B.Kref_dev; s.Kref_ket = K.Kref_dev;
     // The far-field list pays where Boys + R dominate a primitive quartet (L <= 3); above that the extra launch per
     // class pair costs more than the table branch it saves.  MMDB_NO_FAR_LIST / MMDB_FAR_MAXL: A/B switches.
-    if (split && far_enabled(B.la + B.lb + K.la + K.lb)) {
+    const int Ltot = am_of(B.la) + am_of(B.lb) + am_of(K.la) + am_of(K.lb);
+    if (split && !gc && far_enabled(Ltot)) {
         s.sbase_bra = B.sbase_dev; s.sgeo_bra = B.sgeo_dev; s.spmin_bra = B.spmin_dev; s.geo_ket = K.geo_dev; s.pmin_ket = K.pmin_dev;
     }
-    s.tmax = (double)boys_tmax_i(B.la + B.lb + K.la + K.lb) + 0.5;     // margin: rounding of the bounding-sphere distances
+    s.tmax = (double)boys_tmax_i(Ltot) + 0.5;     // margin: rounding of the bounding-sphere distances
     s.nbra = B.npairs; s.row0 = row0; s.row1 = row1; s.same_class = same ? 1 : 0;
-    s.shard = shard; s.nshards = nshards; s.nshell = b->nshell; s.all_pass = all_pass ? 1 : 0;
-    s.DS = b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list_far = list_far; s.list_near = list_near;
+    s.shard = shard; s.nshards = nshards; s.nshell = gc ? b->nshellg : b->nshell; s.all_pass = all_pass ? 1 : 0;
+    s.DS = gc ? b->DSg_dev : b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list_far = list_far; s.list_near = list_near;
     s.ctr = b->ctr_dev + CTR_PER_LAUNCH * slot;
     s.early = getenv("MMDB_SCREEN_NO_EARLY_EXIT") ? 0 : 1;
-    s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = b->sh_bf0_dev; s.cap = cap;
+    s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = gc ? b->shg_bf0_dev : b->sh_bf0_dev; s.cap = cap;
     const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
     const long long nblk = (long long)(row1 - row0) * ntile;
     const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 32);
@@ -975,22 +1169,53 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     const size_t N2 = (size_t)N * N;
     dabs_kernel<<<b->nsm * 4, 256, 0, st>>>(dP_re_dev, dP_im_dev, N2, b->Dabs_dev);
     CU(cudaMemsetAsync(b->dglob_dev, 0, sizeof(unsigned long long), st));
+    // Grouped shell list (S2 pseudo-shells: generally contracted s functions share their primitive integrals) unless the
+    // basis has none, the caller asks for the plain classes (flags bit 2: statistics in the reference's own units,
+    // per-class timing of the plain kernels) or MMDB_NO_GC is set (A/B switch).
+    // The grouped classes serve the class pairs whose bra AND ket are s/p-only pairs — (ss|ss), (ps|ss), (ps|ps) in the
+    // reference's terms, where deep s contractions dominate the work; every class pair with a pp/ds/dp/dd bra runs on
+    // the plain classes (measured: an S2 bra against a wide ket only adds registers).  As sets of function pairs the
+    // grouped classes {ss, ps, S2 s, S2 p, S2 S2} and the plain classes {ss, ps} are the same, so the split is exact.
+    const bool gc = b->have_gc && !(flags & 4) && !getenv("MMDB_NO_GC");
+    if (gc)
+        dshell_kernel<<<(b->nshellg * b->nshellg + 127) / 128, 128, 0, st>>>(b->Dabs_dev, N, b->shg_bf0_dev, b->shg_nf_dev,
+                                                                             b->nshellg, b->DSg_dev, b->dglob_dev);
     dshell_kernel<<<(b->nshell * b->nshell + 127) / 128, 128, 0, st>>>(b->Dabs_dev, N, b->sh_bf0_dev, b->sh_nf_dev,
                                                                        b->nshell, b->DS_dev, b->dglob_dev);
     CU(cudaMemsetAsync(b->ctr_dev, 0, sizeof(unsigned long long) * b->nctr, st));
-    struct Launch { int cb, ck, slot; cudaEvent_t e0, em, e1; };
+    struct Launch { PairClass *B, *K; bool gc; int slot; cudaEvent_t e0, em, e1; };
     std::vector<Launch> launches;
     const bool timing = (flags & 1) != 0;
     // Two queues.  Class pairs with few candidates (the d-heavy classes: a few thousand to a few million
     // quartets) cannot fill 148 SMs and are bounded by the latency of their longest thread; they run on an
     // auxiliary stream with their own list buffer, concurrently with the big classes on the caller's stream.
     // With per-class event timing everything stays on one stream.
-    struct Task { int cb, ck, row0, row1; size_t cap; bool aux; };
+    struct Task { PairClass *B, *K; bool gc; int row0, row1; size_t cap; bool aux; };
     std::vector<Task> tasks;
     size_t cap_main = 0, cap_aux = 0;
-    for (int cb = 0; cb < MMDB_NCLASS_PAIR; ++cb)
-        for (int ck = 0; ck <= cb; ++ck) {
-            PairClass &B = b->pc[cb], &K = b->pc[ck];
+    std::vector<std::pair<PairClass *, PairClass *>> cpairs;
+    std::vector<char> cpair_gc;
+    if (gc) {
+        // KET = the more deeply contracted class of the two (the ket primitive loop is warp-uniform and amortises the
+        // per-bra-primitive work; measured: an S2 bra against a shallow ket costs 1.3-1.9x per primitive quartet), in
+        // the order S2 S2 (<= 64 primitive pairs), S2 s, S2 p (<= 24), ss, ps (<= 9)
+        // — except between two S2 classes, where the deeper one is the BRA: bra pairs are cut into slices of <= 8
+        // primitive pairs, and these small class pairs need the entries more than the amortisation
+        const int by_depth[5] = {8, 6, 7, 0, 1};
+        for (int x = 0; x < 5; ++x)
+            for (int y = x; y < 5; ++y) {
+                const bool both_s2 = y < 3 && !(x == 1 && y == 2);      // (S2 p | S2 s) keeps its measured orientation
+                if (both_s2) cpairs.push_back({&b->pcg[by_depth[x]], &b->pcg[by_depth[y]]});
+                else cpairs.push_back({&b->pcg[by_depth[y]], &b->pcg[by_depth[x]]});
+                cpair_gc.push_back(1);
+            }
+    }
+    for (int cb = gc ? 2 : 0; cb < MMDB_NCLASS_PAIR; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) { cpairs.push_back({&b->pc[cb], &b->pc[ck]}); cpair_gc.push_back(0); }
+    for (size_t cp = 0; cp < cpairs.size(); ++cp) {
+        {
+            PairClass &B = *cpairs[cp].first, &K = *cpairs[cp].second;
+            const bool tgc = cpair_gc[cp] != 0;
             if (B.npairs == 0 || K.npairs == 0) continue;
             // rows of this shard only count towards the list capacity
             size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.slice_entries * (size_t)nshards);
@@ -998,10 +1223,11 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
                 const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.slice_entries;   // room for every slice
-                tasks.push_back(Task{cb, ck, row0, row1, cap, small});
+                tasks.push_back(Task{&B, &K, tgc, row0, row1, cap, small});
                 (small ? cap_aux : cap_main) = std::max(small ? cap_aux : cap_main, cap);
             }
         }
+    }
     // Screening pipeline: the main queue's lists are double-buffered and the screen of task m+1 runs on its own
     // stream while the ERI kernels of task m execute (it fills the SMs the persistent ERI grid vacates at its tail
     // instead of serialising behind it).  Per-class event timing keeps everything on one stream.
@@ -1062,7 +1288,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     for (int pass = 0; pass < 2; ++pass)
         for (const Task &t : tasks) {
             if (t.aux != (pass == 0)) continue;
-            PairClass &B = b->pc[t.cb], &K = b->pc[t.ck];
+            PairClass &B = *t.B, &K = *t.K;
             const bool piped = pipeline && !t.aux;
             cudaStream_t s1 = t.aux ? sa : ((piped && (m_main & 1)) ? st2 : st);
             uint2 *list = t.aux ? list_aux : list_main[piped ? (m_main & 1) : 0];
@@ -1073,7 +1299,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                 ev_done = b->ev_pool[2 * m_main + 1];
                 if (m_main >= 2) CU(cudaStreamWaitEvent(ss, b->ev_pool[2 * (m_main - 2) + 1], 0));   // buffer consumed
             }
-            Launch ln{t.cb, t.ck, slot, nullptr, nullptr, nullptr};
+            Launch ln{t.B, t.K, t.gc, slot, nullptr, nullptr, nullptr};
             if (timing) {
                 CU(cudaEventCreate(&ln.e0));
                 CU(cudaEventCreate(&ln.em));
@@ -1081,9 +1307,9 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                 CU(cudaEventRecord(ln.e0, s1));
             }
             uint2 *list_far = list, *list_near = list + cap_region[t.aux ? 1 : 0];
-            CHK(run_screen(b, B, K, t.cb == t.ck, t.row0, t.row1, shard, nshards, false, tol, slot, true,
+            CHK(run_screen(b, B, K, t.B == t.K, t.row0, t.row1, shard, nshards, false, tol, slot, true,
                            dP_im_dev != nullptr || (flags & 2) != 0,
-                           (long long)t.cap, list_far, list_near, s_scr));
+                           (long long)t.cap, list_far, list_near, s_scr, t.gc));
             if (piped) {
                 CU(cudaEventRecord(ev_ready, ss));
                 CU(cudaStreamWaitEvent(s1, ev_ready, 0));
@@ -1092,14 +1318,16 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             EriArgs a;
             std::memset(&a, 0, sizeof(a));
             a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
-            a.same_class = (t.cb == t.ck);
+            a.braW = B.wgt_soa_dev; a.ketW = K.wgt_dev;
+            a.same_class = (t.B == t.K);
             a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
             a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
             a.dg.fixed = (flags & 2) ? 1 : 0;
             // far-field list (asymptotic Boys branch only), near list, then the slow list (diagonal-type quartets /
             // complex density / deterministic mode)
             a.list = list_far; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_FAR;
-            if (far_enabled(B.la + B.lb + K.la + K.lb)) CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST_FAR, 0, s1));
+            const bool use_far = !t.gc && far_enabled(B.la + B.lb + K.la + K.lb);
+            if (use_far) CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST_FAR, 0, s1));
             a.list = list_near; a.list_step = 1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_NEAR;
             CHK(launch_eri(b, B.la, B.lb, K.la, K.lb, a, LK_DIGEST, 0, s1));
             a.list = list_near + (t.cap - 1); a.list_step = -1; a.count_dev = b->ctr_dev + CTR_PER_LAUNCH * slot + CTR_SLOW;
@@ -1126,28 +1354,43 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         CU(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof(*stats));
         stats->launches = 2;                                   // dabs + dshell, then per task: screen + far? + near + slow
-        for (auto &ln : launches) stats->launches += 3 + (far_enabled(b->pc[ln.cb].la + b->pc[ln.cb].lb + b->pc[ln.ck].la + b->pc[ln.ck].lb) ? 1 : 0);
+        stats->launches += gc ? 1 : 0;
+        for (auto &ln : launches) stats->launches += 3 + ((!ln.gc && far_enabled(ln.B->la + ln.B->lb + ln.K->la + ln.K->lb)) ? 1 : 0);
         for (auto &ln : launches) {
-            const PairClass &B = b->pc[ln.cb], &K = b->pc[ln.ck];
+            const PairClass &B = *ln.B, &K = *ln.K;
             const int64_t nq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_NQUART];
             const int64_t npq = (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_PRIMQ];
             stats->slow_quartets += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_SLOW];
             stats->far_entries += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_FAR];
             stats->near_entries += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_NEAR];
-            const int64_t nfn = (int64_t)ncart(B.la) * ncart(B.lb) * ncart(K.la) * ncart(K.lb);
+            // statistics are kept in the reference's units: an S2 shell counts as its two s shells (quartets and
+            // primitive quartets are summed over the member contractions by the screening kernel), and the class of a
+            // grouped pair is the plain class of its members
+            int pb = pc_index(am_of(B.la), am_of(B.lb)), pk = pc_index(am_of(K.la), am_of(K.lb));
+            int fla = am_of(B.la), flb = am_of(B.lb), flc = am_of(K.la), fld = am_of(K.lb);
+            if (pb < pk) { std::swap(pb, pk); std::swap(fla, flc); std::swap(flb, fld); }
+            const int cidx = pb * MMDB_NCLASS_PAIR + pk;
+            const int64_t nfn = (int64_t)ncart(fla) * ncart(flb) * ncart(flc) * ncart(fld);
             stats->candidates += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_CAND];
             stats->quartets += nq;
             stats->prim_quartets += npq;
+            stats->exec_prim_quartets += (int64_t)ctr[CTR_PER_LAUNCH * ln.slot + CTR_EXECPQ];
             stats->fn_quartets += nq * nfn;
-            stats->model_flops += (double)npq * mmdb_class_flops(B.la, B.lb, K.la, K.lb) + 13.0 * (double)(nq * nfn);
-            stats->class_quartets[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += nq;
-            stats->class_prim_quartets[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += npq;
+            stats->model_flops += (double)npq * mmdb_class_flops(fla, flb, flc, fld) + 13.0 * (double)(nq * nfn);
+            stats->class_quartets[cidx] += nq;
+            stats->class_prim_quartets[cidx] += npq;
             if (timing) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, ln.em, ln.e1);
-                stats->class_ms[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += ms;
-                cudaEventElapsedTime(&ms, ln.e0, ln.em);
-                stats->class_screen_ms[ln.cb * MMDB_NCLASS_PAIR + ln.ck] += ms;
+                stats->class_ms[cidx] += ms;
+                float ms_scr = 0.f;
+                cudaEventElapsedTime(&ms_scr, ln.e0, ln.em);
+                stats->class_screen_ms[cidx] += ms_scr;
+                if (getenv("MMDB_TRACE_LAUNCHES"))      // per-launch table (the grouped classes are folded into the plain ones in stats)
+                    fprintf(stderr, "launch (%d%d|%d%d) %s entries near %llu slow %llu  quartets %lld  prim quartets %lld (evaluated %llu)  screen %.3f ms  eri %.3f ms\n",
+                            B.la, B.lb, K.la, K.lb, ln.gc ? "grouped" : "plain", ctr[CTR_PER_LAUNCH * ln.slot + CTR_NEAR],
+                            ctr[CTR_PER_LAUNCH * ln.slot + CTR_SLOW], (long long)nq, (long long)npq,
+                            ctr[CTR_PER_LAUNCH * ln.slot + CTR_EXECPQ], ms_scr, ms);
             }
         }
     } else if (timing) {
@@ -1228,6 +1471,7 @@ extern "C" int mmdb_set_schwarz_host(mmdb_basis *b, const double *Q_tri)
         qs_chunk_max_kernel<<<((P.npairs + 255) / 256 + 3) / 4, 128>>>(P.Qs_dev, P.npairs, P.Qmax_dev);
     }
     CU(cudaGetLastError());
+    CHK(gc_refresh_bounds(b, nullptr));
     CU(cudaDeviceSynchronize());
     b->have_schwarz = true;
     return MMDB_OK;

@@ -34,10 +34,11 @@ class FockStats(C.Structure):
         ("class_screen_ms", C.c_float * (NCLASS_PAIR * NCLASS_PAIR)),
         ("far_entries", C.c_int64),
         ("near_entries", C.c_int64),
+        ("exec_prim_quartets", C.c_int64),
     ]
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k in ("candidates", "quartets", "prim_quartets", "fn_quartets", "slow_quartets", "launches", "model_flops", "far_entries", "near_entries")}
+        d = {k: getattr(self, k) for k in ("candidates", "quartets", "prim_quartets", "fn_quartets", "slow_quartets", "launches", "model_flops", "far_entries", "near_entries", "exec_prim_quartets")}
         names = ["ss", "ps", "pp", "ds", "dp", "dd"]
         per = {}
         for cb in range(NCLASS_PAIR):
