@@ -709,9 +709,12 @@ __global__ void dshell_kernel(const double *Dabs, int N, const int *bf0, const i
     const int total = nshell * nshell;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
         const int A = x / nshell, B = x % nshell;
+        // symmetric in (A, B) also for a non-Hermitian dP: the screen may then read row C of the table where it needs
+        // column C (a superset test either way; the digestion applies the reference's per-function criterion exactly)
         double m = 0.0;
         for (int a = 0; a < nf[A]; ++a)
-            for (int c = 0; c < nf[B]; ++c) m = fmax(m, Dabs[(size_t)(bf0[A] + a) * N + bf0[B] + c]);
+            for (int c = 0; c < nf[B]; ++c)
+                m = fmax(m, fmax(Dabs[(size_t)(bf0[A] + a) * N + bf0[B] + c], Dabs[(size_t)(bf0[B] + c) * N + bf0[A] + a]));
         DS[x] = m;
         atomicMax(dglob, (unsigned long long)__double_as_longlong(m));
     }
@@ -754,6 +757,9 @@ struct ScreenArgs {
     int early;                     // warp-level early exit on the chunk maxima of the bra bounds
     int split;                     // direct build: one entry per slice, classified into the far / near / slow lists
     int force_slow;                // complex density / deterministic mode: everything goes to the slow list
+    int ds_cache;                  // the two density-bound rows of the ket pair's shells are staged in shared memory (2 * nshell floats)
+    int want_stats;                // keep the statistics counters (candidates, quartets, primitive quartets): four more
+                                   // same-address atomics per tile, only paid when the caller asked for mmdb_fock_stats
     const int *bf0;                // first function index per shell
     long long cap;                 // capacity of list_near (the slow list starts at list_near[cap-1] and grows downwards)
     const double *DS;
@@ -762,7 +768,7 @@ struct ScreenArgs {
     uint2 *list_far, *list_near;
     unsigned long long *ctr;       // see CTR_* below
 };
-enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_EXECPQ = 6, CTR_PER_LAUNCH = 7 };
+enum { CTR_NEAR = 0, CTR_PRIMQ = 1, CTR_CAND = 2, CTR_SLOW = 3, CTR_NQUART = 4, CTR_FAR = 5, CTR_EXECPQ = 6, CTR_WORK = 7, CTR_PER_LAUNCH = 8 };
 
 constexpr int SCR_THREADS = 256;
 #ifndef MMDB_SCR_CPT
@@ -770,6 +776,7 @@ constexpr int SCR_THREADS = 256;
 #endif
 constexpr int SCR_CPT = MMDB_SCR_CPT;
 constexpr int SCR_TILE = SCR_THREADS * SCR_CPT;
+constexpr int SCR_SEG = 4;         // consecutive tiles of one row per work item
 constexpr int SCR_MAXSL = 8;       // slices per pair the classification masks can hold (pairs with more go near/slow whole)
 
 __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
@@ -780,14 +787,20 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
     __shared__ unsigned s_wcand[SCR_THREADS / 32];
     __shared__ unsigned long long s_base[3];
     __shared__ unsigned short s_slot[SCR_THREADS / 32][SCR_CPT * 32];    // compacted phase-1 survivors per warp
+    extern __shared__ float s_ds[];         // [2][nshell]: rows cd.x and cd.y of the shell-block density bounds, rounded up
     const int ntile = (s.nbra + SCR_TILE - 1) / SCR_TILE;
-    const long long nblk = (long long)(s.row1 - s.row0) * ntile;
+    // work item of a block = SCR_SEG consecutive tiles of one row (the staged density rows serve all of them)
+    const int nseg = (ntile + SCR_SEG - 1) / SCR_SEG;
+    const long long nblk = (long long)(s.row1 - s.row0) * nseg * SCR_SEG;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double dg4 = 0.0;
     if (!s.all_pass) dg4 = 4.0 * __longlong_as_double((long long)*s.dglob);
-    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int j = s.row0 + (int)(blk / ntile);
-        const int c0 = (int)(blk % ntile) * SCR_TILE;
+    int staged_j = -1;
+    for (long long blk = (long long)blockIdx.x * SCR_SEG; blk < nblk; blk = ((blk % SCR_SEG) == SCR_SEG - 1) ? blk + 1 + (long long)(gridDim.x - 1) * SCR_SEG : blk + 1) {
+        const int j = s.row0 + (int)(blk / (nseg * SCR_SEG));
+        const int tile = (int)(blk % (nseg * SCR_SEG));
+        if (tile >= ntile) continue;
+        const int c0 = tile * SCR_TILE;
         if (s.nshards > 1 && (j % s.nshards) != s.shard) continue;
         const int cstart = s.same_class ? j : 0;
         if (c0 + SCR_TILE <= cstart) continue;
@@ -799,7 +812,7 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
             for (int ch = c0 >> 8; ch <= ((c0 + SCR_TILE - 1) >> 8); ++ch)
                 if (ch * 256 < s.nbra && !(s.Qmax_bra[ch] * qj * dg4 < s.tol)) tile_live = true;
             if (!tile_live) {
-                if (threadIdx.x == 0) {
+                if (threadIdx.x == 0 && s.want_stats) {
                     const int lo = max(c0, cstart), hi = min(c0 + SCR_TILE, s.nbra);
                     if (hi > lo) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)(hi - lo));
                 }
@@ -811,6 +824,18 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
         const unsigned long long kj = (unsigned long long)(krj & 0xffffffu);
         const unsigned mj = krj >> 24;
         const unsigned long long kxj = (unsigned long long)s.K_ket[j];
+        // The four cross terms of the density test read DS[A or B][C or D]: rows C and D of the (symmetric) table serve
+        // every column of the tile, so they are staged once — the test then costs one gather from L2 (DS[A][B]) and
+        // four from shared memory instead of five from L2 (ncu: long-scoreboard stalls on exactly these loads).
+        if (s.ds_cache && !s.all_pass && staged_j != j) {
+            staged_j = j;
+            const int ns = s.nshell;
+            for (int x = threadIdx.x; x < ns; x += SCR_THREADS) {
+                s_ds[x] = __double2float_ru(s.DS[(size_t)cd.x * ns + x]);
+                s_ds[ns + x] = __double2float_ru(s.DS[(size_t)cd.y * ns + x]);
+            }
+            __syncthreads();
+        }
         // Two phases per warp (128 consecutive columns).  Phase 1: the cheap density-independent bound on all columns,
         // lane-strided (coalesced), survivors compacted into a per-warp slot array in column order.  Phase 2: the
         // six-block density test, slicing and list classification on the compacted survivors only.
@@ -861,8 +886,11 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                     const double *DS = s.DS;
                     const int ns = s.nshell;
                     double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
-                    dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
-                                           fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
+                    if (s.ds_cache)
+                        dmax = fmax(dmax, (double)fmaxf(fmaxf(s_ds[ab.x], s_ds[ns + ab.x]), fmaxf(s_ds[ab.y], s_ds[ns + ab.y])));
+                    else
+                        dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
+                                               fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
                     pass = !(qq * dmax < s.tol);
                 }
                 if (pass) {
@@ -932,14 +960,16 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                 tc += s_wcand[w] & 0xffffu;
                 tq += s_wcand[w] >> 16;
             }
-            if (tq) atomicAdd(s.ctr + CTR_NQUART, (unsigned long long)tq);
+            if (tq && s.want_stats) atomicAdd(s.ctr + CTR_NQUART, (unsigned long long)tq);
             const unsigned tf = (unsigned)(tot & 0x1fffffull), tn = (unsigned)((tot >> 21) & 0x1fffffull), tsl = (unsigned)(tot >> 42);
             s_base[0] = tf ? atomicAdd(s.ctr + CTR_FAR, (unsigned long long)tf) : 0ull;
             s_base[1] = tn ? atomicAdd(s.ctr + CTR_NEAR, (unsigned long long)tn) : 0ull;
             s_base[2] = tsl ? atomicAdd(s.ctr + CTR_SLOW, (unsigned long long)tsl) : 0ull;
-            if (tk) atomicAdd(s.ctr + CTR_PRIMQ, tk);
-            if (tx) atomicAdd(s.ctr + CTR_EXECPQ, tx);
-            if (tc) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)tc);
+            if (s.want_stats) {
+                if (tk) atomicAdd(s.ctr + CTR_PRIMQ, tk);
+                if (tx) atomicAdd(s.ctr + CTR_EXECPQ, tx);
+                if (tc) atomicAdd(s.ctr + CTR_CAND, (unsigned long long)tc);
+            }
         }
         __syncthreads();
         if (bits) {
@@ -959,6 +989,191 @@ __global__ void __launch_bounds__(SCR_THREADS) screen_kernel(const ScreenArgs s)
                 }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-autonomous variant of the screen for direct builds (no far lists): no block-wide barrier, no per-tile atomics.
+// ncu on screen_kernel: barrier stalls were 8 of its 13 cycles per issued instruction — every 1024-column tile ends in
+// a block-wide scan, a serial section of thread 0 and three to seven same-address atomics with a return value.  Here a
+// warp draws chunks of consecutive (ket row, 1024 bra columns) items from a work counter, runs the same two-phase test
+// on 128 columns at a time, and collects its entries in a private shared-memory buffer of SW_BUF entries that it
+// flushes with ONE atomic (space reservation) and a coalesced copy.  Consecutive items share the ket row, so a flushed
+// block is almost always one row: the ERI kernels still see warp-uniform ket pairs (a block boundary inside a warp of
+// theirs costs that one warp the uniform fast path, about one warp in twenty).  Slow-list entries are rare and go out
+// with a warp-aggregated atomic as they appear.
+// ------------------------------------------------------------------------------------------
+constexpr int SW_WARPS = 8;
+constexpr int SW_COLS = 32 * SCR_CPT;     // columns per warp step
+constexpr int SW_ITEM = 1024;             // columns per work item
+constexpr int SW_CHUNK = 4;               // consecutive items per draw from the work counter
+constexpr int SW_BUF = 256;                // entries per warp buffer (a step that produces more goes straight to the list)
+
+__global__ void __launch_bounds__(SW_WARPS * 32) screen_warp_kernel(const ScreenArgs s)
+{
+    extern __shared__ uint2 sw_buf[];                         // [SW_WARPS][SW_BUF]
+    __shared__ unsigned short s_slot[SW_WARPS][SW_COLS];      // compacted phase-1 survivors per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 *buf = sw_buf + warp * SW_BUF;
+    unsigned fill = 0;
+    const int ntile = (s.nbra + SW_ITEM - 1) / SW_ITEM;
+    // rows of this shard: j = jfirst + r * nshards
+    int jfirst = s.row0;
+    while (s.nshards > 1 && (jfirst % s.nshards) != s.shard) ++jfirst;
+    const int nrows = jfirst < s.row1 ? (s.row1 - jfirst + s.nshards - 1) / s.nshards : 0;
+    const long long nitems = (long long)nrows * ntile;
+    double dg4 = 0.0;
+    if (!s.all_pass) dg4 = 4.0 * __longlong_as_double((long long)*s.dglob);
+    unsigned long long st_kk = 0, st_kx = 0, st_cand = 0, st_quart = 0;      // statistics, flushed once per warp
+
+    auto flush = [&]() {
+        if (fill == 0) return;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(s.ctr + CTR_NEAR, (unsigned long long)fill);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (unsigned x = lane; x < fill; x += 32) s.list_near[base + x] = buf[x];
+        __syncwarp();
+        fill = 0;
+    };
+
+    for (;;) {
+        long long it0 = 0;
+        if (lane == 0) it0 = (long long)atomicAdd(s.ctr + CTR_WORK, (unsigned long long)SW_CHUNK);
+        it0 = __shfl_sync(0xffffffffu, it0, 0);
+        if (it0 >= nitems) break;
+        const long long it1 = min(it0 + SW_CHUNK, nitems);
+        for (long long it = it0; it < it1; ++it) {
+            const int j = jfirst + (int)(it / ntile) * s.nshards;
+            const int c0 = (int)(it % ntile) * SW_ITEM;
+            const int cstart = s.same_class ? j : 0;
+            if (c0 + SW_ITEM <= cstart) continue;
+            const double qj = s.Qs_ket[j];
+            const int2 cd = s.sh_ket[j];
+            const unsigned krj = (unsigned)s.Kref_ket[j];
+            const unsigned long long kj = (unsigned long long)(krj & 0xffffffu);
+            const unsigned mj = krj >> 24;
+            const unsigned long long kxj = (unsigned long long)s.K_ket[j];
+            const int hiK = max(s.bf0[cd.x], s.bf0[cd.y]);
+            for (int wbase = c0; wbase < min(c0 + SW_ITEM, s.nbra); wbase += SW_COLS) {
+                if (wbase + SW_COLS <= cstart) continue;
+                // columns [wbase, wbase + 128) lie in one 256-pair chunk of the bra bounds
+                const bool live = s.all_pass || !s.early || !(s.Qmax_bra[wbase >> 8] * qj * dg4 < s.tol);
+                unsigned total = 0;
+#pragma unroll
+                for (int k = 0; k < SCR_CPT; ++k) {
+                    const int off = k * 32 + lane;
+                    const int i = wbase + off;
+                    const bool cand = (i < s.nbra) && (i >= cstart);
+                    st_cand += cand ? 1u : 0u;
+                    bool p1 = cand && live;
+                    if (p1 && !s.all_pass) p1 = !(s.Qs_bra[i] * qj * dg4 < s.tol);
+                    const unsigned m = __ballot_sync(0xffffffffu, p1);
+                    if (p1) s_slot[warp][total + __popc(m & ((1u << lane) - 1u))] = (unsigned short)off;
+                    total += __popc(m);
+                }
+                if (total == 0) continue;
+                __syncwarp();
+                const unsigned per = (total + 31u) >> 5;      // survivors per lane (<= SCR_CPT)
+                unsigned nsl[SCR_CPT], slowm = 0, n_near = 0, n_slow = 0;
+                int col[SCR_CPT];
+#pragma unroll
+                for (int k = 0; k < SCR_CPT; ++k) {
+                    nsl[k] = 0;
+                    col[k] = 0;
+                    const unsigned n = lane * per + k;
+                    if ((unsigned)k < per && n < total) {
+                        const int i = wbase + s_slot[warp][n];
+                        bool pass = true;
+                        int2 ab = s.sh_bra[i];
+                        if (!s.all_pass) {
+                            const double qq = s.Qs_bra[i] * qj;
+                            const double *DS = s.DS;
+                            const int ns = s.nshell;
+                            double dmax = fmax(4.0 * DS[ab.x * ns + ab.y], 4.0 * DS[cd.x * ns + cd.y]);
+                            dmax = fmax(dmax, fmax(fmax(DS[ab.x * ns + cd.x], DS[ab.x * ns + cd.y]),
+                                                   fmax(DS[ab.y * ns + cd.x], DS[ab.y * ns + cd.y])));
+                            pass = !(qq * dmax < s.tol);
+                        }
+                        if (pass) {
+                            col[k] = i;
+                            const int kb = s.K_bra[i];
+                            const unsigned krb = (unsigned)s.Kref_bra[i];
+                            st_kk += (unsigned long long)(krb & 0xffffffu) * kj;
+                            st_quart += (krb >> 24) * mj;
+                            st_kx += (unsigned long long)kb * kxj;
+                            nsl[k] = (unsigned)((kb + BRA_SLICE - 1) / BRA_SLICE);
+                            // block digestion needs different leading shells in bra and ket (kernels_a.cuh)
+                            const bool slow = s.force_slow || max(s.bf0[ab.x], s.bf0[ab.y]) == hiK;
+                            if (slow) { slowm |= 1u << k; n_slow += nsl[k]; }
+                            else n_near += nsl[k];
+                        }
+                    }
+                }
+                __syncwarp();          // s_slot is rewritten by the next step
+                // warp-wide exclusive scan of the near-entry counts
+                unsigned incl = n_near;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const unsigned tot_near = __shfl_sync(0xffffffffu, incl, 31);
+                if (fill + tot_near > (unsigned)SW_BUF) flush();
+                if (tot_near <= (unsigned)SW_BUF) {
+                    unsigned pos = fill + incl - n_near;
+#pragma unroll
+                    for (int k = 0; k < SCR_CPT; ++k)
+                        if (nsl[k] && !(slowm & (1u << k)))
+                            for (unsigned sl = 0; sl < nsl[k]; ++sl) buf[pos++] = make_uint2((unsigned)col[k] | (sl << SLICE_SHIFT), (unsigned)j);
+                    fill += tot_near;
+                } else {
+                    // pairs with more than SCR_MAXSL slices (contractions deeper than 64 primitive pairs): straight to the list
+                    unsigned long long nbase = 0;
+                    if (lane == 0) nbase = atomicAdd(s.ctr + CTR_NEAR, (unsigned long long)tot_near);
+                    nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                    unsigned long long pos = nbase + incl - n_near;
+#pragma unroll
+                    for (int k = 0; k < SCR_CPT; ++k)
+                        if (nsl[k] && !(slowm & (1u << k)))
+                            for (unsigned sl = 0; sl < nsl[k]; ++sl) s.list_near[pos++] = make_uint2((unsigned)col[k] | (sl << SLICE_SHIFT), (unsigned)j);
+                }
+                // slow entries: rare (diagonal-type quartets) unless the whole build is forced onto the slow list
+                if (__any_sync(0xffffffffu, n_slow != 0)) {
+                    unsigned sincl = n_slow;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned v = __shfl_up_sync(0xffffffffu, sincl, o);
+                        if (lane >= o) sincl += v;
+                    }
+                    const unsigned tot_slow = __shfl_sync(0xffffffffu, sincl, 31);
+                    unsigned long long sbase = 0;
+                    if (lane == 0) sbase = atomicAdd(s.ctr + CTR_SLOW, (unsigned long long)tot_slow);
+                    sbase = __shfl_sync(0xffffffffu, sbase, 0);
+                    long long spos = s.cap - 1 - (long long)(sbase + sincl - n_slow);
+#pragma unroll
+                    for (int k = 0; k < SCR_CPT; ++k)
+                        if (nsl[k] && (slowm & (1u << k)))
+                            for (unsigned sl = 0; sl < nsl[k]; ++sl) s.list_near[spos--] = make_uint2((unsigned)col[k] | (sl << SLICE_SHIFT), (unsigned)j);
+                }
+            }
+        }
+    }
+    flush();
+    if (s.want_stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_kk += __shfl_xor_sync(0xffffffffu, st_kk, o);
+            st_kx += __shfl_xor_sync(0xffffffffu, st_kx, o);
+            st_cand += __shfl_xor_sync(0xffffffffu, st_cand, o);
+            st_quart += __shfl_xor_sync(0xffffffffu, st_quart, o);
+        }
+        if (lane == 0) {
+            if (st_kk) atomicAdd(s.ctr + CTR_PRIMQ, st_kk);
+            if (st_kx) atomicAdd(s.ctr + CTR_EXECPQ, st_kx);
+            if (st_cand) atomicAdd(s.ctr + CTR_CAND, st_cand);
+            if (st_quart) atomicAdd(s.ctr + CTR_NQUART, st_quart);
+        }
     }
 }
 
@@ -1083,7 +1298,7 @@ static bool far_enabled(int L)
 
 static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int row0, int row1, int shard, int nshards,
                       bool all_pass, double tol, int slot, bool split, bool force_slow, long long cap, uint2 *list_far,
-                      uint2 *list_near, cudaStream_t st, bool gc = false)
+                      uint2 *list_near, cudaStream_t st, bool gc = false, bool want_stats = true)
 {
     ScreenArgs s;
     std::memset(&s, 0, sizeof(s));
@@ -1101,11 +1316,28 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
     s.DS = gc ? b->DSg_dev : b->DS_dev; s.dglob = b->dglob_dev; s.tol = tol; s.list_far = list_far; s.list_near = list_near;
     s.ctr = b->ctr_dev + CTR_PER_LAUNCH * slot;
     s.early = getenv("MMDB_SCREEN_NO_EARLY_EXIT") ? 0 : 1;
+    s.want_stats = want_stats ? 1 : 0;
     s.split = split ? 1 : 0; s.force_slow = force_slow ? 1 : 0; s.bf0 = gc ? b->shg_bf0_dev : b->sh_bf0_dev; s.cap = cap;
     const long long ntile = (B.npairs + SCR_TILE - 1) / SCR_TILE;
-    const long long nblk = (long long)(row1 - row0) * ntile;
+    const long long nblk = (long long)(row1 - row0) * ((ntile + SCR_SEG - 1) / SCR_SEG);      // work items: SCR_SEG tiles of one row
     const int grid = (int)std::min<long long>(nblk, (long long)b->nsm * 32);
-    if (grid > 0) screen_kernel<<<grid, SCR_THREADS, 0, st>>>(s);
+    // MMDB_SCREEN_WARPS=1: the warp-autonomous kernel (measured slower, 14.1 against 10.6 ms of screening per build: it
+    // removes the barriers but not the latency of the density gathers, and its buffers cost occupancy)
+    if (split && s.sgeo_bra == nullptr && getenv("MMDB_SCREEN_WARPS")) {
+        static bool attr_set = false;
+        const size_t smem = sizeof(uint2) * SW_WARPS * SW_BUF;
+        if (!attr_set) {
+            cudaFuncSetAttribute(screen_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        const long long items = ((long long)(row1 - row0) / nshards + 1) * ((B.npairs + SW_ITEM - 1) / SW_ITEM);
+        const int gridw = (int)std::min<long long>((items + SW_CHUNK * SW_WARPS - 1) / (SW_CHUNK * SW_WARPS), (long long)b->nsm * 4);
+        if (gridw > 0) screen_warp_kernel<<<gridw, SW_WARPS * 32, smem, st>>>(s);
+    } else if (grid > 0) {
+        const size_t smem_ds = (s.nshell <= 4096 && !getenv("MMDB_SCREEN_NO_DS_CACHE")) ? sizeof(float) * 2 * (size_t)s.nshell : 0;
+        s.ds_cache = smem_ds ? 1 : 0;
+        screen_kernel<<<grid, SCR_THREADS, smem_ds, st>>>(s);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MMDB_ERR_CUDA, std::string("screen kernel: ") + cudaGetErrorString(e));
     return MMDB_OK;
@@ -1309,7 +1541,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             uint2 *list_far = list, *list_near = list + cap_region[t.aux ? 1 : 0];
             CHK(run_screen(b, B, K, t.B == t.K, t.row0, t.row1, shard, nshards, false, tol, slot, true,
                            dP_im_dev != nullptr || (flags & 2) != 0,
-                           (long long)t.cap, list_far, list_near, s_scr, t.gc));
+                           (long long)t.cap, list_far, list_near, s_scr, t.gc, stats != nullptr));
             if (piped) {
                 CU(cudaEventRecord(ev_ready, ss));
                 CU(cudaStreamWaitEvent(s1, ev_ready, 0));
