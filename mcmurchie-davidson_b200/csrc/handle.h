@@ -33,6 +33,12 @@ struct ShellH {
     int id = 0;                    // shell id the pair headers carry (index into the list's bf0 / density-block tables)
 };
 
+// Auxiliary streams of a direct build.  Small class pairs are bounded by the latency of their longest thread (a deeply
+// contracted S2 quartet, a (dd|dd) block), not by throughput: on ONE extra stream their floors add up — at eight shards
+// that queue, not the big classes, was the critical path (shard 0 of 8: 12.8 ms against 8.8 ideal).
+constexpr int MMDB_NAUX = 8;       // streams created; MMDB_NAUX_DEFAULT of them used unless the environment says otherwise
+constexpr int MMDB_NAUX_DEFAULT = 4;
+
 // pair classes of the GROUPED shell list of the direct Fock build: the six plain ones + (S2 s), (S2 p), (S2 S2).
 // An (S2, d) pair is expanded into its two plain (d s) pairs.
 constexpr int MMDB_NCLASS_GC = 9;
@@ -91,8 +97,8 @@ struct mmdb_basis {
     size_t list_cap = 0;
     unsigned long long *ctr_dev = nullptr;        // counters
     int nctr = 0;
-    cudaStream_t aux_stream = nullptr;            // small class pairs run here, concurrently with the big ones
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux_stream[MMDB_NAUX] = {nullptr};   // small class pairs run here, concurrently with the big ones and with each other
+    cudaEvent_t ev_fork = nullptr, ev_join[MMDB_NAUX] = {nullptr};
     cudaStream_t main2_stream = nullptr;          // odd main-queue class pairs run here: their grids fill the SMs the previous pair's tail vacates
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaStream_t scr_stream = nullptr;            // screening of the NEXT class pair runs here, one task ahead of the ERI kernels
@@ -100,7 +106,7 @@ struct mmdb_basis {
     std::vector<cudaEvent_t> ev_pool;             // per-task "list ready" / "list consumed" events of the screening pipeline
     double *scratch_dev = nullptr;
     size_t scratch_cap = 0;   // doubles
-    double *eri_scratch_dev = nullptr;            // [3 regions][54 * nsm * 2048] contracted-block columns of the scratch_out classes (main / aux / second main stream)
+    double *eri_scratch_dev = nullptr;            // [2 + MMDB_NAUX regions][54 * nsm * 2048] contracted-block columns of the scratch_out classes (main / second main / auxiliary streams)
     double *stage_host = nullptr, *stage_dev = nullptr;   // mmdb_formPT_host staging: 4 planes of N^2 doubles each (page-locked / device)
     size_t stage_n = 0;
 };

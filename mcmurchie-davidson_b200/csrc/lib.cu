@@ -110,7 +110,7 @@ static size_t eri_scratch_region(const mmdb_basis *b) { return (size_t)54 * b->n
 static int ensure_eri_scratch(mmdb_basis *b)
 {
     if (b->eri_scratch_dev) return MMDB_OK;
-    CU(cudaMalloc(&b->eri_scratch_dev, 3 * eri_scratch_region(b) * sizeof(double)));
+    CU(cudaMalloc(&b->eri_scratch_dev, (2 + MMDB_NAUX) * eri_scratch_region(b) * sizeof(double)));
     return MMDB_OK;
 }
 
@@ -143,7 +143,10 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     cudaFree(b->ctr_dev); cudaFree(b->scratch_dev); cudaFree(b->eri_scratch_dev);
     if (b->stage_host) cudaFreeHost(b->stage_host);
     cudaFree(b->stage_dev);
-    if (b->aux_stream) { cudaStreamDestroy(b->aux_stream); cudaEventDestroy(b->ev_fork); cudaEventDestroy(b->ev_join); }
+    if (b->aux_stream[0]) {
+        cudaEventDestroy(b->ev_fork);
+        for (int x = 0; x < MMDB_NAUX; ++x) { cudaStreamDestroy(b->aux_stream[x]); cudaEventDestroy(b->ev_join[x]); }
+    }
     if (b->scr_stream) { cudaStreamDestroy(b->scr_stream); cudaEventDestroy(b->ev_fork_scr); }
     if (b->main2_stream) { cudaStreamDestroy(b->main2_stream); cudaEventDestroy(b->ev_fork2); cudaEventDestroy(b->ev_join2); }
     for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
@@ -612,8 +615,11 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
     const int L = am_of(la) + am_of(lb) + am_of(lc) + am_of(ld);      // la..ld are shell type codes
     a.boys_tab = b->boys_dev[L];
     CHK(ensure_eri_scratch(b));
-    a.scratch = b->eri_scratch_dev + ((b->aux_stream != nullptr && st == b->aux_stream) ? eri_scratch_region(b)
-                                       : ((b->main2_stream != nullptr && st == b->main2_stream) ? 2 * eri_scratch_region(b) : 0));
+    int region = 0;                      // scratch columns per stream: caller's, second main, auxiliary streams
+    if (b->main2_stream != nullptr && st == b->main2_stream) region = 1;
+    for (int x = 0; x < MMDB_NAUX; ++x)
+        if (b->aux_stream[x] != nullptr && st == b->aux_stream[x]) region = 2 + x;
+    a.scratch = b->eri_scratch_dev + (size_t)region * eri_scratch_region(b);
     const int key = ((la * 4 + lb) * 4 + lc) * 4 + ld;
     cudaError_t e = cudaSuccess;
     const int gridA = b->nsm;   // x occupancy inside launch_class
@@ -1451,7 +1457,8 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             if (B.npairs == 0 || K.npairs == 0) continue;
             // rows of this shard only count towards the list capacity
             size_t rows_per = std::max<size_t>(1, LIST_CAP / (size_t)B.slice_entries * (size_t)nshards);
-            const bool small = !timing && (size_t)B.npairs * K.npairs / nshards <= AUX_MAX_CANDIDATES;
+            const size_t aux_max = getenv("MMDB_AUX_MAX") ? (size_t)atoll(getenv("MMDB_AUX_MAX")) : AUX_MAX_CANDIDATES;
+            const bool small = !timing && (size_t)B.npairs * K.npairs / nshards <= aux_max;
             for (int row0 = 0; row0 < K.npairs; row0 += (int)rows_per) {
                 const int row1 = (int)std::min<size_t>(K.npairs, row0 + rows_per);
                 const size_t cap = (size_t)((row1 - row0 + nshards - 1) / nshards + 1) * B.slice_entries;   // room for every slice
@@ -1465,21 +1472,22 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
     // instead of serialising behind it).  Per-class event timing keeps everything on one stream.
     const bool pipeline = !timing;
     // every region holds a far list [cap] followed by a near list [cap] (whose tail end is the slow list)
-    CHK(ensure_list(b, 2 * ((pipeline ? 2 : 1) * cap_main + cap_aux)));    // [main 0 | main 1 | aux] regions of one buffer
+    CHK(ensure_list(b, 2 * ((pipeline ? 2 : 1) * cap_main + MMDB_NAUX * cap_aux)));    // [main 0 | main 1 | aux 0..] regions of one buffer
     uint2 *list_main[2] = {b->list_dev, b->list_dev + (pipeline ? 2 * cap_main : 0)};
     uint2 *list_aux = b->list_dev + (pipeline ? 2 : 1) * 2 * cap_main;
     const size_t cap_region[2] = {cap_main, cap_aux};
     if ((int)tasks.size() * CTR_PER_LAUNCH > b->nctr) return fail(MMDB_ERR_NOMEM, "mmdb_fock_direct: counter slots exhausted");
-    cudaStream_t sa = st;
+    const int naux = getenv("MMDB_NAUX") ? std::max(1, std::min(MMDB_NAUX, atoi(getenv("MMDB_NAUX")))) : MMDB_NAUX_DEFAULT;
     if (cap_aux > 0) {
-        if (!b->aux_stream) {
-            CU(cudaStreamCreateWithFlags(&b->aux_stream, cudaStreamNonBlocking));
+        if (!b->aux_stream[0]) {
             CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+            for (int x = 0; x < MMDB_NAUX; ++x) {
+                CU(cudaStreamCreateWithFlags(&b->aux_stream[x], cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&b->ev_join[x], cudaEventDisableTiming));
+            }
         }
-        sa = b->aux_stream;
         CU(cudaEventRecord(b->ev_fork, st));           // density screens + zeroed counters are ready
-        CU(cudaStreamWaitEvent(sa, b->ev_fork, 0));
+        for (int x = 0; x < naux; ++x) CU(cudaStreamWaitEvent(b->aux_stream[x], b->ev_fork, 0));
     }
     cudaStream_t ss = st;
     size_t n_main = 0;
@@ -1515,15 +1523,16 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
         CU(cudaStreamWaitEvent(st2, b->ev_fork2, 0));
     }
     int slot = 0;
-    size_t m_main = 0;
+    size_t m_main = 0, m_aux = 0;
     // aux tasks first: they are enqueued (and start) while the host is still launching the big classes
     for (int pass = 0; pass < 2; ++pass)
         for (const Task &t : tasks) {
             if (t.aux != (pass == 0)) continue;
             PairClass &B = *t.B, &K = *t.K;
             const bool piped = pipeline && !t.aux;
-            cudaStream_t s1 = t.aux ? sa : ((piped && (m_main & 1)) ? st2 : st);
-            uint2 *list = t.aux ? list_aux : list_main[piped ? (m_main & 1) : 0];
+            const int aux_id = t.aux ? (int)(m_aux++ % (size_t)naux) : 0;      // tasks of one auxiliary stream share its list region, in order
+            cudaStream_t s1 = t.aux ? b->aux_stream[aux_id] : ((piped && (m_main & 1)) ? st2 : st);
+            uint2 *list = t.aux ? list_aux + (size_t)aux_id * 2 * cap_aux : list_main[piped ? (m_main & 1) : 0];
             cudaStream_t s_scr = piped ? ss : s1;
             cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
             if (piped) {
@@ -1573,8 +1582,10 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             ++slot;
         }
     if (cap_aux > 0) {
-        CU(cudaEventRecord(b->ev_join, sa));
-        CU(cudaStreamWaitEvent(st, b->ev_join, 0));    // everything enqueued after this call sees the full G
+        for (int x = 0; x < naux; ++x) {
+            CU(cudaEventRecord(b->ev_join[x], b->aux_stream[x]));
+            CU(cudaStreamWaitEvent(st, b->ev_join[x], 0));    // everything enqueued after this call sees the full G
+        }
     }
     if (st2 != st) {
         CU(cudaEventRecord(b->ev_join2, st2));
