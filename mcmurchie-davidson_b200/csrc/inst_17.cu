@@ -1,0 +1,5 @@
+// (pp|ds): the narrow pair as the bra (see SWAPPED in lib.cu)
+#include "kernels_a.cuh"
+namespace mmdb {
+MMDB_INSTANTIATE_CLASS(1, 1, 2, 0)
+}

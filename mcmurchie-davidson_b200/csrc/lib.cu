@@ -601,6 +601,7 @@ DECL(2, 1, 0, 0) DECL(2, 1, 1, 0) DECL(2, 1, 1, 1) DECL(2, 1, 2, 0)
 DECL(2, 2, 0, 0) DECL(2, 2, 1, 0)
 DECL(2, 1, 2, 1) DECL(2, 2, 1, 1) DECL(2, 2, 2, 0) DECL(2, 2, 2, 1) DECL(2, 2, 2, 2)
 // classes with an S2 pseudo-shell (type code 3): direct Fock build only; ket = the more deeply contracted pair
+DECL(1, 0, 2, 1) DECL(1, 1, 2, 0)
 DECL(0, 0, 3, 0) DECL(1, 0, 3, 0) DECL(3, 0, 3, 0)
 DECL(0, 0, 3, 1) DECL(1, 0, 3, 1) DECL(3, 1, 3, 0) DECL(3, 1, 3, 1)
 DECL(0, 0, 3, 3) DECL(1, 0, 3, 3) DECL(3, 3, 3, 0) DECL(3, 3, 3, 1) DECL(3, 3, 3, 3)
@@ -634,6 +635,7 @@ static int launch_eri(mmdb_basis *b, int la, int lb, int lc, int ld, EriArgs &a,
             CASE(2, 1, 0, 0) CASE(2, 1, 1, 0) CASE(2, 1, 1, 1) CASE(2, 1, 2, 0)
             CASE(2, 2, 0, 0) CASE(2, 2, 1, 0)
             CASE(2, 1, 2, 1) CASE(2, 2, 1, 1) CASE(2, 2, 2, 0) CASE(2, 2, 2, 1) CASE(2, 2, 2, 2)
+            CASE(1, 0, 2, 1) CASE(1, 1, 2, 0)
             CASE(0, 0, 3, 0) CASE(1, 0, 3, 0) CASE(3, 0, 3, 0)
             CASE(0, 0, 3, 1) CASE(1, 0, 3, 1) CASE(3, 1, 3, 0) CASE(3, 1, 3, 1)
             CASE(0, 0, 3, 3) CASE(1, 0, 3, 3) CASE(3, 3, 3, 0) CASE(3, 3, 3, 1) CASE(3, 3, 3, 3)
@@ -1351,6 +1353,9 @@ static int run_screen(mmdb_basis *b, PairClass &B, PairClass &K, bool same, int 
 
 static const size_t LIST_CAP = (size_t)1 << 27;      // entries per screening chunk (1 GiB of uint2)
 static const size_t SCRATCH_CAP = (size_t)1 << 27;   // doubles (1 GiB)
+// measured on (H2O)32/cc-pVDZ: (ps|dp) 6.3 -> 5.5 ms, (pp|ds) 3.9 -> 2.7 ms; the other six candidates lose ((pp|dp) 4.8 -> 6.0,
+// (ds|dp) 3.0 -> 4.9, (ps|dd) 1.6 -> 3.7, (pp|dd) 1.35 -> 1.7, (ds|dd) 1.0 -> 1.8, (dp|dd) 1.3 -> 1.8: more ket-component chunks)
+static const char *SWAPPED = "41,32";
 static const size_t AUX_MAX_CANDIDATES = (size_t)6 << 20;   // class pairs up to this many candidates per shard go to the aux stream
 
 extern "C" int mmdb_eri_dense(mmdb_basis *b, double *TwoE_dev, void *stream)
@@ -1448,8 +1453,21 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
                 cpair_gc.push_back(1);
             }
     }
+    // Orientation of the plain class pairs: by default the pair of the higher class is the bra; for the class pairs in
+    // SWAPPED the NARROW pair is the bra (fewer Hermite rows and fewer bra components per thread: smaller register
+    // blocks, fewer ket-component chunks).  MMDB_SWAP="41,32,..." (bra class, ket class digits) overrides the list.
+    // (Also measured: pp / ds / dp bras against the ss-type kets of the grouped list, i.e. S2 kets under a wide bra:
+    // (pp|ss) 3.73 -> 4.0 ms, (ds|ss) 3.35 -> 3.7, (dp|ss) 2.0 -> 2.5 — three launches of 232-255 registers instead of one.)
+    const char *swap_env = getenv("MMDB_SWAP");
+    const char *swap_list = swap_env ? swap_env : SWAPPED;
     for (int cb = gc ? 2 : 0; cb < MMDB_NCLASS_PAIR; ++cb)
-        for (int ck = 0; ck <= cb; ++ck) { cpairs.push_back({&b->pc[cb], &b->pc[ck]}); cpair_gc.push_back(0); }
+        for (int ck = 0; ck <= cb; ++ck) {
+            const char tok[3] = {(char)('0' + cb), (char)('0' + ck), 0};
+            const bool swp = strstr(swap_list, tok) != nullptr;
+            if (swp) cpairs.push_back({&b->pc[ck], &b->pc[cb]});
+            else cpairs.push_back({&b->pc[cb], &b->pc[ck]});
+            cpair_gc.push_back(0);
+        }
     for (size_t cp = 0; cp < cpairs.size(); ++cp) {
         {
             PairClass &B = *cpairs[cp].first, &K = *cpairs[cp].second;
