@@ -21,4 +21,6 @@ def formPT(P, P_old, bfs, nbasis, screen, tol):
     if len(bfs) != N or P.shape != (N, N) or P_old.shape != (N, N):
         raise ValueError("formPT: inconsistent nbasis / matrix shapes")
     eng = _engine.engine_for(bfs)
-    return eng.formPT(P, P_old, screen=screen, tol=float(tol))
+    # no statistics on the reference-facing call: they cost four more atomics per screening tile, a read-back and a
+    # stream synchronisation in the middle of the build (Engine.formPT(..., want_stats=True) keeps them for the tools)
+    return eng.formPT(P, P_old, screen=screen, tol=float(tol), want_stats=False)
