@@ -32,6 +32,13 @@ def main(src, dst):
             la, lb, lc, ld, epi = (int(x) for x in m.groups())
             if epi == 0:
                 continue                      # EPI_STORE launches belong to the Schwarz table, not to the build
+            # shell type code 3 = S2 pseudo-shell (two s contractions): its launches count towards the plain class of the
+            # members, and kernels that run with the narrow pair as the bra are listed under the reference's class name
+            la, lb, lc, ld = (0 if x == 3 else x for x in (la, lb, lc, ld))
+            la, lb = max(la, lb), min(la, lb)
+            lc, ld = max(lc, ld), min(lc, ld)
+            if la * (la + 1) // 2 + lb < lc * (lc + 1) // 2 + ld:
+                la, lb, lc, ld = lc, ld, la, lb
             key = "(%s%s|%s%s)" % (NAMES[la], NAMES[lb], NAMES[lc], NAMES[ld])
         elif "screen_kernel" in name:
             key = "screen_kernel"
