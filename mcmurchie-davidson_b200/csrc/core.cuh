@@ -868,6 +868,7 @@ struct EriArgs {
     const double *braS;           // structure-of-arrays copy of the bra primitive pairs (class kernels), see BraSrc
     const long long *braRow;
     long long braN;
+    const double *braPQ;          // direct builds: per bra pair {dP block, sqrt(Q) block} in component order, packed per build (or nullptr)
     const double *braW;           // weights of bra pairs with an S2 member: [MAX_WGT][braN], rows as braS (or nullptr)
     const PairHdr *ketH;
     const PrimPair *ketP;

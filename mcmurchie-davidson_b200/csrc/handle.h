@@ -66,6 +66,7 @@ struct PairClass {
     double *Qs_dev = nullptr;   // [npairs]
     double *Qmax_dev = nullptr; // [ceil(npairs/256)] maxima of Qs over 256-pair chunks (screening early-exit)
     int *K_dev = nullptr;       // [npairs] primitive pairs per shell pair
+    double *PQ_dev = nullptr;   // [npairs][2 * nab] the pair's own dP block and sqrt(Q) block, packed at the start of every direct build
     int *Kref_dev = nullptr;    // [npairs] statistics: primitive pairs summed over the member contractions | members << 24
     double *wgt_dev = nullptr;      // pairs with an S2 member: [nprimpairs][MAX_WGT] contraction weights (ket side)
     double *wgt_soa_dev = nullptr;  // the same as [MAX_WGT][nprimpairs] in the rows of prim_soa_dev (bra side)

@@ -178,7 +178,7 @@ __device__ __forceinline__ DigestGeom make_geom(int N, int bfA, int bfB, int bfC
 
 template <int LA, int LB, int LC, int LD, int CD0, int NCDC>
 __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestGeom &g, bool active, bool ket_uniform,
-                                             const double (&out)[ncomp(LA) * ncomp(LB) * NCDC])
+                                             const double (&out)[ncomp(LA) * ncomp(LB) * NCDC], const double *__restrict__ pq)
 {
     constexpr int NA = ncomp(LA), NB = ncomp(LB), NC = ncomp(LC), ND = ncomp(LD);
     // which c / d components this chunk touches
@@ -227,7 +227,9 @@ __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestG
                 constexpr int ab = a * NB + b;
                 constexpr double sab = cscale(LA, a) * cscale(LB, b);
                 const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
-                const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
+                // the bra pair's own density and Schwarz blocks come packed per pair (one or two sectors instead of one
+                // sector per element: these kernels are L2-bound on exactly such gathers, profiles/r02_ncu_final_summary.txt)
+                const double pab = pq ? __ldg(pq + ab) : __ldg(&P[oab]), qab = pq ? __ldg(pq + NA * NB + ab) : __ldg(&SQ[oab]);
                 const double pab4 = 4.0 * fabs(pab);
                 double wab = 1.0;
                 if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
@@ -305,7 +307,8 @@ __device__ __forceinline__ void digest_block(const DigestArgs &dg, const DigestG
 // unrolled digestion was the bulk of the instruction footprint (ncu: stall_no_instruction dominant).
 template <int LA, int LB, int LC, int LD>
 __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB, int bfC, int bfD, int c, int d, double scd,
-                                          bool active, bool ket_uniform, const double *__restrict__ out, long long ostride)
+                                          bool active, bool ket_uniform, const double *__restrict__ out, long long ostride,
+                                          const double *__restrict__ pq)
 {
     constexpr int NA = ncomp(LA), NB = ncomp(LB);
     const DigestGeom g = make_geom(dg.N, bfA, bfB, bfC, bfD);
@@ -347,7 +350,7 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
                 constexpr int b = decltype(B_)::value;
                 constexpr double s8 = 8.0 * cscale(LA, a) * cscale(LB, b);
                 const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
-                const double pab = __ldg(&P[oab]), qab = __ldg(&SQ[oab]);
+                const double pab = pq ? __ldg(pq + a * NB + b) : __ldg(&P[oab]), qab = pq ? __ldg(pq + NA * NB + a * NB + b) : __ldg(&SQ[oab]);
                 double wab = 1.0;
                 if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
                 const double dmax = fmax(4.0 * fabs(pab), fmax(ma, Mb[b]));
@@ -407,6 +410,8 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
     constexpr int NA = ncomp(LA), NB = ncomp(LB), NC = ncomp(LC), ND = ncomp(LD);
     constexpr int NAB = NA * NB, NCD = NC * ND;
     double out[NAB * NCDC];
+    // packed {dP, sqrt(Q)} blocks of the bra pair (direct builds; nullptr otherwise)
+    const double *pq = a.braPQ ? a.braPQ + (size_t)ibra * (2 * NAB) : nullptr;
     constexpr bool SCR = scratch_out<LA, LB, LC, LD>();
     // scratch column of this thread: element x at scr[x * sstride] (coalesced across the threads of the grid)
     const long long sstride = (long long)gridDim.x * blockDim.x;
@@ -437,7 +442,7 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
                 constexpr int cd = CD0 + cdi;
                 digest_cd_rt<LA, LB, LC, LD>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, cd / ND, cd % ND,
                                              cscale(LC, cd / ND) * cscale(LD, cd % ND), valid, ket_uniform,
-                                             scr + (long long)cdi * sstride, (long long)NCDC * sstride);
+                                             scr + (long long)cdi * sstride, (long long)NCDC * sstride, pq);
             });
         } else {
             if (valid) {
@@ -475,11 +480,11 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
 #pragma unroll
                 for (int x = 0; x < NAB; ++x) tmp[x] = out[x * NCDC + cdi];
                 digest_cd_rt<LA, LB, LC, LD>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, cd / ND, cd % ND,
-                                             cscale(LC, cd / ND) * cscale(LD, cd % ND), valid, ket_uniform, tmp, 1);
+                                             cscale(LC, cd / ND) * cscale(LD, cd % ND), valid, ket_uniform, tmp, 1, pq);
             });
         } else {
             const DigestGeom geom = make_geom(a.dg.N, bh.bfA, bh.bfB, kh.bfA, kh.bfB);
-            digest_block<LA, LB, LC, LD, CD0, NCDC>(a.dg, geom, valid, ket_uniform, out);
+            digest_block<LA, LB, LC, LD, CD0, NCDC>(a.dg, geom, valid, ket_uniform, out, pq);
         }
     } else {
         // second list (diagonal-type quartets, complex densities): per-function digestion, out of line

@@ -133,7 +133,7 @@ extern "C" int mmdb_basis_destroy(mmdb_basis *b)
     auto free_class = [](PairClass &p) {
         cudaFree(p.hdr_dev); cudaFree(p.prim_dev); cudaFree(p.prim_ab_dev); cudaFree(p.prim_soa_dev); cudaFree(p.prim_row_dev); cudaFree(p.Qs_dev); cudaFree(p.Qmax_dev); cudaFree(p.K_dev); cudaFree(p.sh_dev);
         cudaFree(p.sbase_dev); cudaFree(p.sgeo_dev); cudaFree(p.spmin_dev); cudaFree(p.geo_dev); cudaFree(p.pmin_dev);
-        cudaFree(p.Kref_dev); cudaFree(p.wgt_dev); cudaFree(p.wgt_soa_dev);
+        cudaFree(p.Kref_dev); cudaFree(p.wgt_dev); cudaFree(p.wgt_soa_dev); cudaFree(p.PQ_dev);
     };
     for (auto &p : b->pc) free_class(p);
     for (auto &p : b->pcg) free_class(p);
@@ -375,6 +375,7 @@ static int build_pairs(mmdb_basis *b, const std::vector<ShellH> &sh, PairClass *
         CU(cudaMalloc(&P.Qmax_dev, sizeof(double) * ((P.npairs + 255) / 256)));
         CU(cudaMalloc(&P.K_dev, sizeof(int) * P.npairs));
         CU(cudaMalloc(&P.Kref_dev, sizeof(int) * P.npairs));
+        CU(cudaMalloc(&P.PQ_dev, sizeof(double) * (size_t)P.npairs * 2 * ncomp(P.la) * ncomp(P.lb)));
         CU(cudaMemcpy(P.Kref_dev, Kref.data(), sizeof(int) * P.npairs, cudaMemcpyHostToDevice));
         if (weighted) {
             CU(cudaMalloc(&P.wgt_dev, sizeof(double) * wgt.size()));
@@ -702,6 +703,22 @@ __global__ void gc_bounds_kernel(const PairHdr *hdr, int npairs, int ta, int tb,
         for (int a = 0; a < na; ++a)
             for (int c = 0; c < nb; ++c) qmax = fmax(qmax, sqrt(fabs(Q[(size_t)(h.bfA + a) * N + h.bfB + c])));
         Qs[i] = qmax;
+    }
+}
+
+// {dP block, sqrt(Q) block} of every pair of a class in the component order and orientation the block digestion reads
+// them (make_geom: the higher-indexed shell is the row), packed so that a thread finds them in one or two sectors
+__global__ void pack_pair_blocks_kernel(const PairHdr *hdr, int npairs, int ta, int tb, int N, const double *P, const double *SQ,
+                                        double *PQ)
+{
+    const int na = ncomp(ta), nb = ncomp(tb), nab = na * nb;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < (long long)npairs * nab; x += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(x / nab), ab = (int)(x % nab), a = ab / nb, c = ab % nb;
+        const int bfA = hdr[i].bfA, bfB = hdr[i].bfB;
+        const bool aHi = bfA >= bfB;
+        const long long o = aHi ? (long long)(bfA + a) * N + bfB + c : (long long)(bfB + c) * N + bfA + a;
+        PQ[(size_t)i * 2 * nab + ab] = P[o];
+        PQ[(size_t)i * 2 * nab + nab + ab] = SQ[o];
     }
 }
 
@@ -1469,6 +1486,17 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             else cpairs.push_back({&b->pc[cb], &b->pc[ck]});
             cpair_gc.push_back(0);
         }
+    if (!getenv("MMDB_NO_PACKED_BLOCKS")) {
+        std::vector<PairClass *> packed;
+        for (auto &cp : cpairs) {
+            PairClass *B = cp.first;
+            if (B->npairs == 0 || std::find(packed.begin(), packed.end(), B) != packed.end()) continue;
+            packed.push_back(B);
+            const long long work = (long long)B->npairs * ncomp(B->la) * ncomp(B->lb);
+            pack_pair_blocks_kernel<<<(int)std::min<long long>((work + 255) / 256, 2048), 256, 0, st>>>(B->hdr_dev, B->npairs, B->la, B->lb, N, dP_re_dev,
+                                                                                                  b->SQ_dev, B->PQ_dev);
+        }
+    }
     for (size_t cp = 0; cp < cpairs.size(); ++cp) {
         {
             PairClass &B = *cpairs[cp].first, &K = *cpairs[cp].second;
@@ -1579,6 +1607,7 @@ extern "C" int mmdb_fock_direct(mmdb_basis *b, const double *dP_re_dev, const do
             std::memset(&a, 0, sizeof(a));
             a.braH = B.hdr_dev; a.braP = B.prim_dev; a.braS = B.prim_soa_dev; a.braRow = B.prim_row_dev; a.braN = B.nprimpairs; a.ketH = K.hdr_dev; a.ketP = K.prim_dev;
             a.braW = B.wgt_soa_dev; a.ketW = K.wgt_dev;
+            a.braPQ = (dP_im_dev == nullptr && !getenv("MMDB_NO_PACKED_BLOCKS")) ? B.PQ_dev : nullptr;
             a.same_class = (t.B == t.K);
             a.dg.N = N; a.dg.tol = tol; a.dg.SQ = b->SQ_dev; a.dg.Dabs = b->Dabs_dev;
             a.dg.dPre = dP_re_dev; a.dg.dPim = dP_im_dev; a.dg.Gre = G_re_dev; a.dg.Gim = G_im_dev;
