@@ -455,7 +455,7 @@ def main_ours(a):
         fl = c["prim_quartets"] * c["flops_per_prim_quartet"]
         ach = fl / (c["ms"] * 1e-3) / 1e12
         traffic, traffic_src = ncu_traffic(a.workload, world, name)
-        roof = {"bound": "fp64_fma", "kernel": "eri_class_kernel %s fused J/K digestion" % name, "achieved": ach, "peak": peak_tf,
+        roof = {"bound": "fp64_fma", "kernel": "eri_class_kernel launches of class %s (plain + S2 pseudo-shell variants), fused J/K digestion" % name, "achieved": ach, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                 "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of all launches of this class in one build of this workload on one GPU, %s" % traffic_src) if traffic else "no ncu capture of this workload / GPU count committed: null rather than a number from another configuration",
                 "peak_source": "measured live: DFMA issue probe mmdb_fp64_peak (MEASURED_PEAKS.json has no FP64 entry; nominal 37.2)",

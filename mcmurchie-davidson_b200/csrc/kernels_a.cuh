@@ -88,8 +88,14 @@ __host__ __device__ constexpr int ka_threads()
         if (L == 1) return NFN <= 6 ? 512 : (NFN <= 12 ? 384 : 256);
         return 256;
     }
-    if (L == 0) return 768;                      // 80 registers
-    if (L == 1) return 640;                      // 96 registers (768 threads at 80 registers: slower)
+#ifndef MMDB_T_L0
+#define MMDB_T_L0 768
+#endif
+#ifndef MMDB_T_L1
+#define MMDB_T_L1 640
+#endif
+    if (L == 0) return MMDB_T_L0;                // 80 registers
+    if (L == 1) return MMDB_T_L1;                // 96 registers (768 threads at 80 registers: slower)
     if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
     if (L == 2) return 384;                      // (ps|ps), (pp|ss): <= 170 registers
     // lock-step classes, measured per class: one 8-warp CTA per SM (ONE instruction stream per SM, fetched once
