@@ -36,6 +36,23 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.load().mmdb_version() >= 100
 
 
+def test_stats_struct_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of mmdb_fock_stats (mmd/_b200/lib.py) has the size and field offsets the C compiler gives the
+    struct of include/mmdb200.h (a field added on one side only would shift every counter read through the C ABI)."""
+    import ctypes as C
+    import subprocess
+    from mmd._b200 import lib as L
+    src = tmp_path / "layout.c"
+    fields = [f for f, _ in L.FockStats._fields_]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mmdb200.h"\nint main(void){printf("%zu", sizeof(mmdb_fock_stats));'
+                   + "".join('printf(" %%zu", offsetof(mmdb_fock_stats, %s));' % f for f in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got[0] == C.sizeof(L.FockStats)
+    assert got[1:] == [getattr(L.FockStats, f).offset for f in fields]
+
+
 def test_flop_model_matches_survey_table():
     # SURVEY.md §8(d) per-class values
     table = {(0, 0, 0, 0): 59, (1, 0, 0, 0): 101, (1, 0, 1, 0): 213, (1, 1, 0, 0): 259, (1, 1, 1, 0): 581,
