@@ -65,6 +65,9 @@ __host__ __device__ constexpr int chunk_ncd()
 template <int LA, int LB, int LC, int LD>
 __host__ __device__ constexpr bool block_chunks()
 {
+#ifdef MMDB_SERIAL_SCRATCH      // experiment: the scratch-column classes run their chunks serially in the thread (R kept for one-primitive quartets)
+    if (scratch_out<LA, LB, LC, LD>()) return false;
+#endif
     return ncomp(LC) * ncomp(LD) / chunk_ncd<LA, LB, LC, LD>() >= 2;
 }
 
