@@ -210,6 +210,25 @@ class Engine(object):
             self.TwoE_dev = torch.from_numpy(host).to(self.tdev)
         return host
 
+    def dense_device(self):
+        """Fill the dense tensor on the device only (self.TwoE_dev); False when the caller's function order differs from
+        the device order (then dense() with its host-side reordering is the way)."""
+        if not self.table.identity:
+            return False
+        torch = _torch()
+        n = self.Ndev
+        with torch.cuda.device(self.tdev):
+            T = torch.empty((n, n, n, n), dtype=torch.float64, device=self.tdev)
+            L.check(self.lib.mmdb_eri_dense(self.h, L.ptr(T), self._stream()))
+        self.TwoE_dev = T
+        return True
+
+    def dense_host(self):
+        """Host copy of the resident tensor (rebuilt when the engine has none)."""
+        if self.TwoE_dev is None or not self.table.identity:
+            return self.dense(keep_device=True)
+        return self.TwoE_dev.cpu().numpy()
+
     # ---- in-core J/K (mmd/scf.py:97-98) ----------------------------------------------------------
     def jk_incore(self, P, TwoE=None):
         """J, K (complex128 (N,N)) from the dense tensor; P complex or real (N,N), user order."""

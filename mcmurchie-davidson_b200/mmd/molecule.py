@@ -145,9 +145,34 @@ class Molecule(SCF):
         self.U = fractional_matrix_power(self.S, 0.5)
 
     def two_electron_integrals(self):
-        N = self.nbasis
-        self.TwoE = np.zeros((N, N, N, N))
-        self.TwoE = np.asarray(doERIs(N, self.TwoE, self.bfs))
+        """Dense (N,N,N,N) tensor (cython/twoe.pyx:12-31).  The B200 engine fills it ON THE DEVICE, where the in-core
+        J/K, the AO->MO transformation and MP2 read it; the host copy behind `mol.TwoE` (1.66 GB for benzene/6-31G**,
+        seconds of page-able copies) is only made when somebody reads that attribute."""
+        fill = getattr(self.engine, "dense_device", None)
+        if fill is not None and fill():
+            self._TwoE = None
+            self._TwoE_on_device = True
+        else:
+            N = self.nbasis
+            self.TwoE = np.asarray(doERIs(N, np.zeros((N, N, N, N)), self.bfs))
+
+    @property
+    def TwoE(self):
+        if getattr(self, "_TwoE", None) is None:
+            if not getattr(self, "_TwoE_on_device", False):
+                raise AttributeError("TwoE")          # like the reference before build(direct=False): hasattr() is False
+            self._TwoE = np.ascontiguousarray(self.engine.dense_host())
+        return self._TwoE
+
+    @TwoE.setter
+    def TwoE(self, value):
+        self._TwoE = value
+        self._TwoE_on_device = False
+
+    @TwoE.deleter
+    def TwoE(self):
+        self._TwoE = None
+        self._TwoE_on_device = False
 
     def forces(self):
         """Nuclear forces of the converged RHF state (mmd/forces.py of the reference): atom.forces = -dE/dX for every

@@ -16,7 +16,8 @@ class PostSCF(object):
         self.mol = mol
         if not self.mol.is_converged:
             sys.exit("SCF not converged, skipping Post-SCF")
-        if not hasattr(self.mol, "TwoE"):
+        # (the flag first: reading mol.TwoE would copy a device-resident tensor to the host just to see that it exists)
+        if not (getattr(self.mol, "_TwoE_on_device", False) or hasattr(self.mol, "TwoE")):
             sys.exit("Post-SCF needs the in-core tensor: run RHF(direct=False)")
         self.ao2mo()
 
