@@ -23,3 +23,23 @@ os.environ["MMDB_DETERMINISTIC"] = "1"
 m = Molecule(geom, basis)
 m.RHF(doPrint=False, direct=True)
 print("direct deterministic", m.energy.real)
+
+# round 2: forces (gradient kernels), the plain-class build (flags bit 2), the warp-autonomous screen and the far lists
+del os.environ["MMDB_DETERMINISTIC"]
+import numpy as np  # noqa: E402
+m = Molecule(geom, basis)
+m.RHF(doPrint=False, direct=True)
+m.forces()
+print("forces", float(np.abs(np.array([a.forces for a in m.atoms])).max()))
+eng = m.engine
+scr = eng.schwarz()
+P = np.asarray(m.P, dtype=complex)
+Z = np.zeros_like(P)
+G0 = eng.formPT(P, Z, screen=scr, tol=1e-12)
+G1 = eng.formPT(P, Z, screen=scr, tol=1e-12, flags=4)
+os.environ["MMDB_SCREEN_WARPS"] = "1"
+G2 = eng.formPT(P, Z, screen=scr, tol=1e-12)
+del os.environ["MMDB_SCREEN_WARPS"]
+os.environ["MMDB_FAR_MAXL"] = "3"
+G3 = eng.formPT(P, Z, screen=scr, tol=1e-12, flags=4)
+print("grouped vs plain / warp screen / far lists", float(np.abs(G0 - G1).max()), float(np.abs(G0 - G2).max()), float(np.abs(G0 - G3).max()))
