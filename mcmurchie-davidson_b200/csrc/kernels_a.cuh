@@ -10,6 +10,14 @@
 namespace mmdb {
 
 constexpr int KA_THREADS = 128;
+// compile-time A/B hooks (profiles/README.md): CTA sizes of the (ss|ss) / (ps|ss) kernels; -DMMDB_SERIAL_SCRATCH runs the
+// ket chunks of the scratch-column classes serially in the thread
+#ifndef MMDB_T_L0
+#define MMDB_T_L0 768
+#endif
+#ifndef MMDB_T_L1
+#define MMDB_T_L1 640
+#endif
 
 // LA..LD are shell TYPE codes (core.cuh: 3 = S2, a two-component s pseudo-shell); ltot = total angular momentum
 __host__ __device__ constexpr int ltot(int la, int lb, int lc, int ld) { return am_of(la) + am_of(lb) + am_of(lc) + am_of(ld); }
@@ -91,12 +99,6 @@ __host__ __device__ constexpr int ka_threads()
         if (L == 1) return NFN <= 6 ? 512 : (NFN <= 12 ? 384 : 256);
         return 256;
     }
-#ifndef MMDB_T_L0
-#define MMDB_T_L0 768
-#endif
-#ifndef MMDB_T_L1
-#define MMDB_T_L1 640
-#endif
     if (L == 0) return MMDB_T_L0;                // 80 registers
     if (L == 1) return MMDB_T_L1;                // 96 registers (768 threads at 80 registers: slower)
     if (L == 2 && LA == 2) return 512;           // (ds|ss): 128 registers
