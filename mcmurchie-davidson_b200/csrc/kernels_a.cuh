@@ -12,6 +12,12 @@ namespace mmdb {
 constexpr int KA_THREADS = 128;
 // compile-time A/B hooks (profiles/README.md): CTA sizes of the (ss|ss) / (ps|ss) kernels; -DMMDB_SERIAL_SCRATCH runs the
 // ket chunks of the scratch-column classes serially in the thread
+// scratch-column classes that digest their three ket component pairs in ONE call (digest_cdn_rt): measured
+// (dp|ds) 2.93 -> 2.59 ms, (dp|dp) 2.56 -> 1.80 ms, but (dp|pp) 4.69 -> 5.25 ms (larger code: that kernel is the one with
+// instruction-fetch stalls) — so the d-ket classes only.  -DMMDB_DIGEST_MULTI=0 / =2 : none / all of them.
+#ifndef MMDB_DIGEST_MULTI
+#define MMDB_DIGEST_MULTI 1
+#endif
 #ifndef MMDB_T_L0
 #define MMDB_T_L0 768
 #endif
@@ -393,6 +399,152 @@ __device__ __noinline__ void digest_cd_rt(const DigestArgs &dg, int bfA, int bfB
     }
 }
 
+// Several consecutive ket component pairs of ONE thread at once (the scratch-column classes hold three): the bra pair's
+// blocks are loaded once, J_ab is summed over the ket components before its reduction (a third of the J_ab reductions
+// of three digest_cd_rt calls), the per-a integrals are loaded together.  Element (ab, cdi) at out[(ab * NCX + cdi) * ostride].
+template <int LA, int LB, int LC, int LD, int NCX>
+__device__ __noinline__ void digest_cdn_rt(const DigestArgs &dg, int bfA, int bfB, int bfC, int bfD, int cd0, bool active,
+                                           bool ket_uniform, const double *__restrict__ out, long long ostride,
+                                           const double *__restrict__ pq)
+{
+    constexpr int NA = ncomp(LA), NB = ncomp(LB), ND = ncomp(LD);
+    const DigestGeom g = make_geom(dg.N, bfA, bfB, bfC, bfD);
+    const double *__restrict__ P = dg.dPre;
+    const double *__restrict__ SQ = dg.SQ;
+    double *__restrict__ G = dg.Gre;
+    int cc[NCX], dd[NCX];
+    long long ocd[NCX];
+    double scd[NCX], jcd[NCX];
+#pragma unroll
+    for (int x = 0; x < NCX; ++x) {
+        const int cd = cd0 + x;
+        cc[x] = cd / ND; dd[x] = cd % ND;
+        ocd[x] = g.cd.base + cc[x] * g.cd.s0 + dd[x] * g.cd.s1;
+        // per-component normalisation of d shells (xx, yy, zz: 1/sqrt(3)), cython/basis.pxi:102-105
+        scd[x] = ((LC == 2 && (cc[x] == 0 || cc[x] == 3 || cc[x] == 5)) ? 0.57735026918962576451 : 1.0) *
+                 ((LD == 2 && (dd[x] == 0 || dd[x] == 3 || dd[x] == 5)) ? 0.57735026918962576451 : 1.0);
+        if (LC == LD && g.sameCD) {      // one shell twice: components c >= d only, half weight on c == d
+            if (cc[x] < dd[x]) scd[x] = 0.0;
+            if (cc[x] == dd[x]) scd[x] *= 0.5;
+        }
+        jcd[x] = 0.0;
+    }
+    const bool same_c = cc[0] == cc[NCX - 1], same_d = ND == 1;       // (consecutive cd: c is non-decreasing)
+    if (active) {
+        const double tol = dg.tol;
+        double pcd[NCX], qcd[NCX], pcd4[NCX], Pbc[NB][NCX], Pbd[NB][NCX], Kbc[NB][NCX], Kbd[NB][NCX], Mb[NB][NCX];
+#pragma unroll
+        for (int x = 0; x < NCX; ++x) {
+            pcd[x] = __ldg(&P[ocd[x]]); qcd[x] = __ldg(&SQ[ocd[x]]);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                Pbc[b][x] = __ldg(&P[g.pbc.base + b * g.pbc.s0 + cc[x] * g.pbc.s1]);
+                Pbd[b][x] = __ldg(&P[g.pbd.base + b * g.pbd.s0 + dd[x] * g.pbd.s1]);
+                Kbc[b][x] = 0.0; Kbd[b][x] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < NCX; ++x) {
+            pcd4[x] = 4.0 * fabs(pcd[x]);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) Mb[b][x] = fmax(fabs(Pbc[b][x]), fabs(Pbd[b][x]));
+        }
+        sfor<0, NA>([&](auto A_) {
+            constexpr int a = decltype(A_)::value;
+            // this row's integrals and density elements first (independent loads, one latency exposure)
+            double ov[NB][NCX], pac[NCX], pad[NCX], kac[NCX], kad[NCX], ma[NCX];
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) ov[b][x] = __ldcg(out + (long long)((a * NB + b) * NCX + x) * ostride);
+#pragma unroll
+            for (int x = 0; x < NCX; ++x) {
+                pac[x] = __ldg(&P[g.pac.base + a * g.pac.s0 + cc[x] * g.pac.s1]);
+                pad[x] = __ldg(&P[g.pad.base + a * g.pad.s0 + dd[x] * g.pad.s1]);
+                kac[x] = 0.0; kad[x] = 0.0;
+            }
+#pragma unroll
+            for (int x = 0; x < NCX; ++x) ma[x] = fmax(pcd4[x], fmax(fabs(pac[x]), fabs(pad[x])));
+            sfor<0, NB>([&](auto B_) {
+                constexpr int b = decltype(B_)::value;
+                constexpr double s8 = 8.0 * cscale(LA, a) * cscale(LB, b);
+                const long long oab = g.ab.base + a * g.ab.s0 + b * g.ab.s1;
+                const double pab = pq ? __ldg(pq + a * NB + b) : __ldg(&P[oab]), qab = pq ? __ldg(pq + NA * NB + a * NB + b) : __ldg(&SQ[oab]);
+                double wab = 1.0;
+                if constexpr (LA == LB) wab = g.sameAB ? (a > b ? 1.0 : (a == b ? 0.5 : 0.0)) : 1.0;
+                const double pab4 = 4.0 * fabs(pab);
+                double jab = 0.0;
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) {
+                    const double dmax = fmax(pab4, fmax(ma[x], Mb[b][x]));
+                    const double bound = (qab * qcd[x]) * dmax;
+                    const double e = (bound < tol) ? 0.0 : (s8 * wab * scd[x]) * ov[b][x];
+                    const double eq = -0.25 * e;
+                    jab = fma(pcd[x], e, jab);
+                    jcd[x] = fma(pab, e, jcd[x]);
+                    kac[x] = fma(Pbd[b][x], eq, kac[x]);
+                    Kbd[b][x] = fma(pac[x], eq, Kbd[b][x]);
+                    kad[x] = fma(Pbc[b][x], eq, kad[x]);
+                    Kbc[b][x] = fma(pad[x], eq, Kbc[b][x]);
+                }
+                red_add_f64(&G[oab], jab);
+            });
+            // consecutive ket component pairs share c (or d): their exchange contributions go to ONE element — one
+            // reduction with the sum instead of NCX back-to-back reductions on the same address
+            if (same_c) {
+                double v = 0.0;
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) v += kac[x];
+                red_add_f64(&G[g.gac.base + a * g.gac.s0 + cc[0] * g.gac.s1], v);
+            } else {
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) red_add_f64(&G[g.gac.base + a * g.gac.s0 + cc[x] * g.gac.s1], kac[x]);
+            }
+            if (same_d) {
+                double v = 0.0;
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) v += kad[x];
+                red_add_f64(&G[g.gad.base + a * g.gad.s0 + dd[0] * g.gad.s1], v);
+            } else {
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) red_add_f64(&G[g.gad.base + a * g.gad.s0 + dd[x] * g.gad.s1], kad[x]);
+            }
+        });
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (same_c) {
+                double v = 0.0;
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) v += Kbc[b][x];
+                red_add_f64(&G[g.gbc.base + b * g.gbc.s0 + cc[0] * g.gbc.s1], v);
+            } else {
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) red_add_f64(&G[g.gbc.base + b * g.gbc.s0 + cc[x] * g.gbc.s1], Kbc[b][x]);
+            }
+            if (same_d) {
+                double v = 0.0;
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) v += Kbd[b][x];
+                red_add_f64(&G[g.gbd.base + b * g.gbd.s0 + dd[0] * g.gbd.s1], v);
+            } else {
+#pragma unroll
+                for (int x = 0; x < NCX; ++x) red_add_f64(&G[g.gbd.base + b * g.gbd.s0 + dd[x] * g.gbd.s1], Kbd[b][x]);
+            }
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < NCX; ++x) {
+        double v = jcd[x];
+        if (ket_uniform) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) red_add_f64(&G[ocd[x]], v);
+        } else if (active) {
+            red_add_f64(&G[ocd[x]], v);
+        }
+    }
+}
+
 template <bool FIXED>
 static __device__ __noinline__ void digest_block_slow(const DigestArgs &dg, const PairHdr &bh, const PairHdr &kh, bool samePair,
                                                int la, int lb, int lc, int ld, int cd0, int ncdc, const double *vals)
@@ -447,6 +599,8 @@ __device__ __forceinline__ void run_chunk(const EriArgs &a, unsigned long long e
                     });
                 });
             }
+        } else if constexpr (EPI == EPI_DIGEST && (MMDB_DIGEST_MULTI == 2 || (MMDB_DIGEST_MULTI == 1 && LC == 2))) {
+            digest_cdn_rt<LA, LB, LC, LD, NCDC>(a.dg, bh.bfA, bh.bfB, kh.bfA, kh.bfB, CD0, valid, ket_uniform, scr, sstride, pq);
         } else if constexpr (EPI == EPI_DIGEST) {
             sfor<0, NCDC>([&](auto CDI) {
                 constexpr int cdi = decltype(CDI)::value;
